@@ -1,0 +1,341 @@
+/*
+ * updes_oracle.c -- TEST INFRASTRUCTURE ONLY (never shipped, never on the product path).
+ *
+ * Plain-C, CPU, FP64 restatement of the dense assembly of ddrous/Updes
+ * (reference: /root/reference/updes/assembly.py, utils.py, operators.py).  Each function
+ * cites the reference lines it follows.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this library.
+ *
+ * The reference differentiates its kernels with JAX autodiff (jax.grad / jax.jacfwd) and
+ * wraps the result in nan_to_num; here the derivatives are written in closed form, with the
+ * r == 0 singularity mapped to 0 exactly as nan_to_num(NaN) does (operators.py:58,:83,:109).
+ * oracle/oracle_ad.py holds a second, autodiff-structured restatement (torch.func) that the
+ * tests use to pin these closed forms.
+ *
+ * PARITY PIN STATUS: the reference cannot be imported here (no jax/jaxlib/lineax in the image)
+ * and its own tests hold no per-entry golden vectors.  This oracle is pinned to (1) the AD
+ * restatement, (2) the three known-answer tests of the reference (updes/tests/test_*.py), and
+ * (3) the analytic Laplace solution of demos/Laplace/00_laplace_with_rbf.py:109-110.
+ * Per-entry parity against the reference's JAX x64 path itself is therefore "parity unpinned".
+ */
+#include <math.h>
+#include <stddef.h>
+#include <string.h>
+
+enum { UO_POLYHARMONIC = 0, UO_THIN_PLATE = 1, UO_GAUSSIAN = 2, UO_MULTIQUADRIC = 3, UO_INV_MULTIQUADRIC = 4 };
+
+/* radial profile and its first two radial derivatives, r > 0 (utils.py:30-69) */
+static void radial(int kind, double p, double r, double *f, double *f1, double *f2)
+{
+    switch (kind) {
+    case UO_POLYHARMONIC: {            /* r**(2a+1), utils.py:50-55 */
+        double e = 2.0 * p + 1.0;
+        *f = pow(r, e);
+        *f1 = e * pow(r, e - 1.0);
+        *f2 = e * (e - 1.0) * pow(r, e - 2.0);
+        break;
+    }
+    case UO_THIN_PLATE: {              /* log(r) * r**(2a), utils.py:63-69 */
+        double e = 2.0 * p, lg = log(r);
+        *f = lg * pow(r, e);
+        *f1 = pow(r, e - 1.0) * (e * lg + 1.0);
+        *f2 = pow(r, e - 2.0) * ((e - 1.0) * (e * lg + 1.0) + e);
+        break;
+    }
+    case UO_GAUSSIAN: {                /* exp(-(eps r)^2), utils.py:44-48 */
+        double e2 = p * p, g = exp(-e2 * r * r);
+        *f = g;
+        *f1 = -2.0 * e2 * r * g;
+        *f2 = (4.0 * e2 * e2 * r * r - 2.0 * e2) * g;
+        break;
+    }
+    case UO_MULTIQUADRIC: {            /* sqrt(1 + (eps r)^2), utils.py:30-35 */
+        double e2 = p * p, s = sqrt(1.0 + e2 * r * r);
+        *f = s;
+        *f1 = e2 * r / s;
+        *f2 = e2 / (s * s * s);
+        break;
+    }
+    default: {                         /* 1/sqrt(1 + (eps r)^2), utils.py:37-42 */
+        double e2 = p * p, s = sqrt(1.0 + e2 * r * r);
+        *f = 1.0 / s;
+        *f1 = -e2 * r / (s * s * s);
+        *f2 = -e2 / (s * s * s) + 3.0 * e2 * e2 * r * r / (s * s * s * s * s);
+        break;
+    }
+    }
+}
+
+/* value of the kernel at r = 0 (thin_plate: nan_to_num(log(0)*0) = 0, utils.py:65) */
+static double radial_at_zero(int kind)
+{
+    return (kind == UO_POLYHARMONIC || kind == UO_THIN_PLATE) ? 0.0 : 1.0;
+}
+
+/*
+ * jet[0..4] = phi, d/dx, d/dy, d2/dx2, d2/dy2 of rbf(x, center) with respect to x
+ * (operators.py:15-111: nodal_value / nodal_gradient / nodal_laplacian / nodal_div_grad).
+ * At r == 0 autodiff through sqrt gives NaN, which nan_to_num turns into 0.
+ */
+void uo_rbf_jet(int kind, double param, double x, double y, double cx, double cy, double *jet)
+{
+    double dx = x - cx, dy = y - cy;
+    double r = sqrt(dx * dx + dy * dy);          /* utils.py:19-22 */
+    if (r == 0.0) {
+        jet[0] = radial_at_zero(kind);
+        jet[1] = jet[2] = jet[3] = jet[4] = 0.0;
+        return;
+    }
+    double f, f1, f2;
+    radial(kind, param, r, &f, &f1, &f2);
+    double ux = dx / r, uy = dy / r;
+    jet[0] = f;
+    jet[1] = f1 * ux;
+    jet[2] = f1 * uy;
+    jet[3] = f2 * ux * ux + (f1 / r) * (1.0 - ux * ux);
+    jet[4] = f2 * uy * uy + (f1 / r) * (1.0 - uy * uy);
+}
+
+/* the 15 monomials of degree <= 4, in the reference's order (utils.py:92-134) */
+static const int MON_EX[15] = {0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 4, 3, 2, 1, 0};
+static const int MON_EY[15] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4};
+
+static double ipow(double x, int e)
+{
+    double v = 1.0;
+    for (int k = 0; k < e; k++) v *= x;
+    return v;
+}
+
+/* jet of monomial `id` at (x, y); plain derivatives, no nan_to_num (operators.py:60,:85,:111) */
+void uo_monomial_jet(int id, double x, double y, double *jet)
+{
+    int a = MON_EX[id], b = MON_EY[id];
+    jet[0] = ipow(x, a) * ipow(y, b);
+    jet[1] = a >= 1 ? a * ipow(x, a - 1) * ipow(y, b) : 0.0;
+    jet[2] = b >= 1 ? b * ipow(x, a) * ipow(y, b - 1) : 0.0;
+    jet[3] = a >= 2 ? a * (a - 1) * ipow(x, a - 2) * ipow(y, b) : 0.0;
+    jet[4] = b >= 2 ? b * (b - 1) * ipow(x, a) * ipow(y, b - 2) : 0.0;
+}
+
+static double dot5(const double *c, const double *jet)
+{
+    return c[0] * jet[0] + c[1] * jet[1] + c[2] * jet[2] + c[3] * jet[3] + c[4] * jet[4];
+}
+
+/* assembly.py:10-36 -- Phi[i, S_i] = rbf(x_i, x_j), S_i = every node but i (cloud.py:110-112, Q1) */
+void uo_assemble_Phi(const double *nodes, int N, int kind, double param, double *Phi)
+{
+    double jet[5];
+    memset(Phi, 0, sizeof(double) * (size_t)N * N);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            Phi[(size_t)i * N + j] = jet[0];
+        }
+}
+
+/* assembly.py:39-59 -- P[i, j] = monomial_j(x_i) */
+void uo_assemble_P(const double *nodes, int N, int M, double *P)
+{
+    double jet[5];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < M; j++) {
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            P[(size_t)i * M + j] = jet[0];
+        }
+}
+
+/* assembly.py:62-85 -- A = [[Phi, P], [P^T, 0]] */
+void uo_assemble_A(const double *nodes, int N, int M, int kind, double param, double *A, double *work_Phi, double *work_P)
+{
+    size_t n = (size_t)N + M;
+    uo_assemble_Phi(nodes, N, kind, param, work_Phi);
+    uo_assemble_P(nodes, N, M, work_P);
+    memset(A, 0, sizeof(double) * n * n);
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < N; j++) A[i * n + j] = work_Phi[(size_t)i * N + j];
+        for (int j = 0; j < M; j++) {
+            A[i * n + N + j] = work_P[(size_t)i * M + j];
+            A[(N + j) * n + i] = work_P[(size_t)i * M + j];
+        }
+    }
+}
+
+/*
+ * assembly.py:93-137 -- internal rows.  The user operator, once lowered, is
+ * c0*phi + c1*phi_x + c2*phi_y + c3*phi_xx + c4*phi_yy with per-row coefficients
+ * rowcoef[i*5 .. i*5+4] (they carry the dependence on fields[i], assembly.py:128,:135).
+ */
+void uo_assemble_op_Phi_P(const double *nodes, int N, int Ni, int M, int kind, double param,
+                          const double *rowcoef, double *opPhi, double *opP)
+{
+    double jet[5];
+    memset(opPhi, 0, sizeof(double) * (size_t)Ni * N);
+    for (int i = 0; i < Ni; i++) {
+        const double *c = rowcoef + 5 * (size_t)i;
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;                      /* support excludes self */
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            opPhi[(size_t)i * N + j] = dot5(c, jet);
+        }
+        for (int j = 0; j < M; j++) {
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            opP[(size_t)i * M + j] = dot5(c, jet);
+        }
+    }
+}
+
+/*
+ * assembly.py:141-362 -- boundary rows, in the order d, n, r, periodic-value rows of every
+ * periodic group, periodic-flux rows of every group.
+ *   normals : sorted_outward_normals, (Nn + Nr + sum(Np)) x 2, indexed [i - Ni - Nd]
+ *   betas   : Robin coefficients per Robin node, length Nr
+ * Robin rows of bdPhi read normals[i - Ni - Nd - Nn] (assembly.py:206), which is the wrong
+ * slot whenever Nn > 0; bdP uses the node's own normal (assembly.py:303).  Reproduced (Q3).
+ */
+void uo_assemble_bd_Phi_P(const double *nodes, int N, int Ni, int Nd, int Nn, int Nr,
+                          const int *Np, int nb_groups, const double *normals, const double *betas,
+                          int M, int kind, double param, double *bdPhi, double *bdP)
+{
+    int sumNp = 0;
+    for (int g = 0; g < nb_groups; g++) sumNp += Np[g];
+    int Nb = Nd + Nn + Nr + sumNp;
+    double jet[5], jet2[5];
+    memset(bdPhi, 0, sizeof(double) * (size_t)Nb * N);
+    memset(bdP, 0, sizeof(double) * (size_t)Nb * M);
+
+    /* Dirichlet, assembly.py:169-176 */
+    for (int i = Ni; i < Ni + Nd; i++)
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            bdPhi[(size_t)(i - Ni) * N + j] = jet[0];
+        }
+    /* Neumann, assembly.py:178-190 */
+    for (int i = Ni + Nd; i < Ni + Nd + Nn; i++) {
+        const double *nv = normals + 2 * (size_t)(i - Ni - Nd);
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            bdPhi[(size_t)(i - Ni) * N + j] = jet[1] * nv[0] + jet[2] * nv[1];
+        }
+    }
+    /* Robin, assembly.py:194-212 (normal slot quirk Q3) */
+    for (int i = Ni + Nd + Nn; i < Ni + Nd + Nn + Nr; i++) {
+        const double *nv = normals + 2 * (size_t)(i - Ni - Nd - Nn);
+        double beta = betas ? betas[i - Ni - Nd - Nn] : 0.0;
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            bdPhi[(size_t)(i - Ni) * N + j] = beta * jet[0] + (jet[1] * nv[0] + jet[2] * nv[1]);
+        }
+    }
+    /* periodic value rows, assembly.py:215-234: all columns written, self included (Q2) */
+    int start = Ni + Nd + Nn + Nr, jump = 0;
+    for (int g = 0; g < nb_groups; g++) {
+        int nc = Np[g] / 2;
+        for (int i = start; i < start + nc; i++) {
+            int i2 = i + nc;
+            for (int j = 0; j < N; j++) {
+                uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+                uo_rbf_jet(kind, param, nodes[2 * i2], nodes[2 * i2 + 1], nodes[2 * j], nodes[2 * j + 1], jet2);
+                bdPhi[(size_t)(i - Ni - jump) * N + j] = jet[0] - jet2[0];
+            }
+        }
+        start += Np[g];
+        jump += nc;
+    }
+    /* periodic flux rows, assembly.py:238-267: grad1.n1 - grad2.(-n2) */
+    start = Ni + Nd + Nn + Nr; jump = 0;
+    for (int g = 0; g < nb_groups; g++) {
+        int nc = Np[g] / 2;
+        for (int i = start; i < start + nc; i++) {
+            int i2 = i + nc;
+            const double *n1 = normals + 2 * (size_t)(i - Ni - Nd);
+            const double *n2 = normals + 2 * (size_t)(i - Ni - Nd + nc);
+            for (int j = 0; j < N; j++) {
+                uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+                uo_rbf_jet(kind, param, nodes[2 * i2], nodes[2 * i2 + 1], nodes[2 * j], nodes[2 * j + 1], jet2);
+                double d1 = jet[1] * n1[0] + jet[2] * n1[1];
+                double d2 = jet2[1] * (-n2[0]) + jet2[2] * (-n2[1]);
+                bdPhi[(size_t)(i - Ni - jump + sumNp / 2) * N + j] = d1 - d2;
+            }
+        }
+        start += Np[g];
+        jump += nc;
+    }
+
+    /* bd(P), assembly.py:274-359 */
+    for (int j = 0; j < M; j++) {
+        for (int i = Ni; i < Ni + Nd; i++) {                               /* :283-287 */
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            bdP[(size_t)(i - Ni) * M + j] = jet[0];
+        }
+        for (int i = Ni + Nd; i < Ni + Nd + Nn; i++) {                     /* :290-299 */
+            const double *nv = normals + 2 * (size_t)(i - Ni - Nd);
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            bdP[(size_t)(i - Ni) * M + j] = jet[1] * nv[0] + jet[2] * nv[1];
+        }
+        for (int i = Ni + Nd + Nn; i < Ni + Nd + Nn + Nr; i++) {           /* :302-316, own normal */
+            const double *nv = normals + 2 * (size_t)(i - Ni - Nd);
+            double beta = betas ? betas[i - Ni - Nd - Nn] : 0.0;
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            bdP[(size_t)(i - Ni) * M + j] = beta * jet[0] + (jet[1] * nv[0] + jet[2] * nv[1]);
+        }
+        int node0 = Ni + Nd + Nn + Nr, row0 = Ni + Nd + Nn + Nr;
+        for (int g = 0; g < nb_groups; g++) {                              /* :319-334 */
+            int nc = Np[g] / 2;
+            for (int k = 0; k < nc; k++) {
+                int i1 = node0 + k, i2 = node0 + nc + k;
+                uo_monomial_jet(j, nodes[2 * i1], nodes[2 * i1 + 1], jet);
+                uo_monomial_jet(j, nodes[2 * i2], nodes[2 * i2 + 1], jet2);
+                bdP[(size_t)(row0 + k - Ni) * M + j] = jet[0] - jet2[0];
+            }
+            row0 += nc;
+            node0 += Np[g];
+        }
+        node0 = Ni + Nd + Nn + Nr; row0 = Ni + Nd + Nn + Nr;
+        for (int g = 0; g < nb_groups; g++) {                              /* :336-359 */
+            int nc = Np[g] / 2;
+            for (int k = 0; k < nc; k++) {
+                int i1 = node0 + k, i2 = node0 + nc + k;
+                const double *n1 = normals + 2 * (size_t)(i1 - Ni - Nd);
+                const double *n2 = normals + 2 * (size_t)(i2 - Ni - Nd);
+                uo_monomial_jet(j, nodes[2 * i1], nodes[2 * i1 + 1], jet);
+                uo_monomial_jet(j, nodes[2 * i2], nodes[2 * i2 + 1], jet2);
+                double d1 = jet[1] * n1[0] + jet[2] * n1[1];
+                double d2 = jet2[1] * (-n2[0]) + jet2[2] * (-n2[1]);
+                bdP[(size_t)(row0 + k - Ni + sumNp / 2) * M + j] = d1 - d2;
+            }
+            row0 += nc;
+            node0 += Np[g];
+        }
+    }
+}
+
+/*
+ * Field evaluators, operators.py:118-147 (value), :156-184 (gradient), :294-330 (laplacian):
+ * out[i*3 + {0,1,2,...}] over evaluation points xs.  `which`: 0 value, 1 d/dx, 2 d/dy, 3 laplacian.
+ * The rbf sum runs over ALL centres, self included (phi(0) kept; derivatives at r=0 -> 0).
+ */
+void uo_eval_field(const double *xs, int nx, const double *centers, int N, int M,
+                   const double *coeffs, int kind, double param, int which, double *out)
+{
+    double jet[5];
+    for (int i = 0; i < nx; i++) {
+        double acc = 0.0;
+        for (int j = 0; j < N; j++) {
+            uo_rbf_jet(kind, param, xs[2 * i], xs[2 * i + 1], centers[2 * j], centers[2 * j + 1], jet);
+            double t = which == 3 ? jet[3] + jet[4] : jet[which];
+            acc += coeffs[j] * t;
+        }
+        for (int j = 0; j < M; j++) {
+            uo_monomial_jet(j, xs[2 * i], xs[2 * i + 1], jet);
+            double t = which == 3 ? jet[3] + jet[4] : jet[which];
+            acc += coeffs[N + j] * t;
+        }
+        out[i] = acc;
+    }
+}
