@@ -1,0 +1,132 @@
+/*
+ * updes_b200.h -- C-ABI of the B200-native Updes hot path (libupdes_b200.so).
+ *
+ * The reference (ddrous/Updes) has no FFI: its boundary is the Python call surface
+ *   pde_solver / pde_solver_jit          updes/operators.py:559-683
+ * whose arithmetic lives in
+ *   assemble_Phi / assemble_P / assemble_A        updes/assembly.py:10-85
+ *   assemble_op_Phi_P / assemble_bd_Phi_P         updes/assembly.py:93-362
+ *   assemble_invert_A / assemble_B                updes/assembly.py:87-90, :366-401
+ *   core_compute_coefficients                     updes/assembly.py:404-410
+ *   lx.linear_solve(..., lx.QR())                 updes/operators.py:612-613
+ *   value / gradient / laplacian / divergence     updes/operators.py:118-351
+ * Each entry point below names the reference code it replaces.  INTEGRATION.md shows the
+ * jax.ffi / ctypes stubs a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is caller-allocated DEVICE memory unless a
+ *     parameter is documented as host; the library never frees caller memory;
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*), no hidden threads;
+ *   - return value: 0 ok; < 0 bad argument (-k = k-th argument); > 0 CUDA runtime error code
+ *     (cudaError_t) raised while enqueuing.  Numerical status (LAPACK-style "zero pivot at
+ *     column k", 1-based) is written to a device int32 `info` so no call forces a sync;
+ *   - matrices are ROW-MAJOR with leading dimension `ld` (elements); `ld` must be a multiple
+ *     of 16 (128-byte rows: TMA tiles, 16-byte vector stores) and the base 1024-byte aligned;
+ *   - all arithmetic is FP64 (reference default, updes/config.py:15-16).
+ */
+#ifndef UPDES_B200_H
+#define UPDES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rbf kinds, updes/utils.py:30-69 (param = a for the first two, eps for the others) */
+enum {
+  UPDES_RBF_POLYHARMONIC = 0,         /* r^(2a+1)            utils.py:50-55 */
+  UPDES_RBF_THIN_PLATE = 1,           /* r^(2a) log r        utils.py:63-69 */
+  UPDES_RBF_GAUSSIAN = 2,             /* exp(-(eps r)^2)     utils.py:44-48 */
+  UPDES_RBF_MULTIQUADRIC = 3,         /* sqrt(1+(eps r)^2)   utils.py:30-35 */
+  UPDES_RBF_INVERSE_MULTIQUADRIC = 4  /* 1/sqrt(1+(eps r)^2) utils.py:37-42 */
+};
+
+/*
+ * Row descriptors of the collocation system (one per collocation row r < N).
+ * A row is  sum over up to two evaluation points p of  c_p . jet(x_p, centre_j)  with
+ * jet = (phi, phi_x, phi_y, phi_xx, phi_yy) taken w.r.t. the evaluation point, derivatives
+ * forced to 0 at r == 0 (the reference's nan_to_num, operators.py:58,:83,:109).  This one form
+ * covers internal operator rows (assembly.py:93-137) and Dirichlet / Neumann / Robin /
+ * periodic rows (assembly.py:141-362); the host layer fills it (updes_b200/assembly.py).
+ */
+typedef struct UpdesRows {
+  const double *pts;        /* [npts x 2] evaluation points (for K: the cloud's sorted_nodes) */
+  const int32_t *p1;        /* [R] index into pts of the first evaluation point */
+  const int32_t *p2;        /* [R] second point or -1 (periodic rows, assembly.py:215-267) */
+  const double *cphi1;      /* [R x 5] coefficients on RBF columns at p1 */
+  const double *cphi2;      /* [R x 5] ... at p2 (read only where p2 >= 0) */
+  const double *cpol1;      /* [R x 5] coefficients on monomial columns at p1 (differs from
+                               cphi1 only for the Robin normal quirk, assembly.py:206 vs :303) */
+  const double *cpol2;      /* [R x 5] ... at p2 */
+  const int32_t *skip;      /* [R] centre index whose column is left 0 (the reference drops a
+                               node from its own support, cloud.py:110-112), or -1 */
+} UpdesRows;
+
+/* ---- assembly (replaces assembly.py:93-362 + the P^T block of :62-85) --------------------
+ * Fills rows [row0, row0+nrows) x columns [0, ld) of the (N+M) x (N+M) collocation matrix
+ *   K = [[op(Phi) op(P)], [bd(Phi) bd(P)], [P^T 0]]            
+ * into `out` (row-major, leading dimension ld, out[0] = K[row0][0]).  Padding columns
+ * [N+M, ld) are zeroed.  centres = sorted_nodes [N x 2].  rows describes collocation rows
+ * 0..N-1 (rows >= N are the P^T rows).  Whole matrix: row0 = 0, nrows = N+M.
+ * jet_mask: which parts of the jet the coefficient rows in the range actually use
+ * (UPDES_JET_VAL | UPDES_JET_GRAD | UPDES_JET_HESS); the kernel is specialised on it so that a
+ * Laplace operator does not pay for phi and grad phi.  0 or 7 = everything.
+ */
+#define UPDES_JET_VAL 1
+#define UPDES_JET_GRAD 2
+#define UPDES_JET_HESS 4
+int updes_assemble_rows(int rbf_kind, double rbf_param, int N, int M, const double *centres,
+                        const UpdesRows *rows, int64_t row0, int64_t nrows, int jet_mask,
+                        double *out, int64_t ld, void *stream);
+
+/* Same entries for an arbitrary rectangular block [row0,row0+nrows) x [col0,col0+ncols)
+ * written to out[(r-row0)*ld + (c-col0)] -- the tile form used by block-cyclic sharding. */
+int updes_assemble_block(int rbf_kind, double rbf_param, int N, int M, const double *centres,
+                         const UpdesRows *rows, int64_t row0, int64_t nrows, int64_t col0,
+                         int64_t ncols, int jet_mask, double *out, int64_t ld, void *stream);
+
+/* ---- matrix-free jets (replaces operators.py:118-351 value/gradient/laplacian and gives
+ * K.c, [Phi P].c without storing a matrix) ---------------------------------------------------
+ * For every evaluation point i < npts and field f < nf:
+ *   jphi[(f*npts + i)*5 + k] = sum_{j<N, j != skip[i]} coeffs[f*ldc + j] * jet_k(pts_i, centre_j)
+ *   jpol[(f*npts + i)*5 + k] = sum_{m<M} coeffs[f*ldc + N + m] * jet_k(monomial_m)(pts_i)
+ * skip may be NULL (no column skipped).  workspace: updes_eval_jets_workspace_bytes().
+ */
+size_t updes_eval_jets_workspace_bytes(int N, int npts, int nf);
+int updes_eval_jets(int rbf_kind, double rbf_param, int N, int M, const double *centres,
+                    const double *coeffs, int64_t ldc, int nf, const double *pts, int npts,
+                    const int32_t *skip, double *jphi, double *jpol, void *workspace, void *stream);
+
+/* ---- dense LU (replaces jnp.linalg.inv + GEMM + lineax QR, assembly.py:87-90,:398-401,
+ * operators.py:612-616, by one factorisation P K = L U) ------------------------
+ * Opaque handle: owns tensor maps and a small device workspace; release with updes_lu_destroy.
+ */
+typedef struct UpdesLU UpdesLU;
+
+int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld);
+int updes_lu_destroy(UpdesLU *handle);
+/* Factor K in place (row-major, partial pivoting by rows).  ipiv[n] (device, int32, 0-based:
+ * row k was exchanged with row ipiv[k]); info (device int32): 0 or 1-based first zero pivot. */
+int updes_lu_factor(UpdesLU *handle, double *K, int32_t *ipiv, int32_t *info, void *stream);
+/* Solve K X = B for nrhs right-hand sides using the factors.  B is [nrhs][ldb] (each
+ * right-hand side contiguous, ldb >= n), overwritten by X.  transpose != 0 solves K^T X = B. */
+int updes_lu_solve(UpdesLU *handle, const double *LU, const int32_t *ipiv, double *B,
+                   int64_t ldb, int nrhs, int transpose, void *stream);
+
+/* Building blocks, exported so tests can pin each kernel against the oracle. */
+int updes_dgemm_sub(UpdesLU *handle, double *K, int64_t rc, int64_t cc, int64_t ra, int64_t ca,
+                    int64_t rb, int64_t cb, int64_t m, int64_t n, int64_t k, void *stream);
+int updes_lu_panel(UpdesLU *handle, double *K, int64_t r0, int64_t nc, int32_t *ipiv,
+                   int32_t *info, void *stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+const char *updes_b200_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t updes_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPDES_B200_H */

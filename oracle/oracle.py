@@ -1,0 +1,449 @@
+"""CPU oracle for the Updes global RBF-collocation path -- TEST INFRASTRUCTURE ONLY.
+
+Restates, on the CPU in FP64, what /root/reference/updes computes on the hot path so the CUDA
+product can be checked against it.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this module; the product
+package ``updes_b200`` never does.
+
+Contents (reference file:line in each docstring):
+  * RefSquareCloud / RefGmshCloud -- literal, dict-and-loop restatement of updes/cloud.py
+  * assemble_* wrappers around oracle/updes_oracle.c (closed-form matrix entries)
+  * assemble_q, reference_solve   -- the reference *formulation*: inv(A), B = D inv(A)[:, :N],
+    QR solve of B u = q, coefficients inv(A)[u; 0]   (assembly.py:366-410, operators.py:602-616)
+
+PARITY PIN STATUS: "parity unpinned" at the per-entry level -- the reference needs jax/jaxlib/
+lineax, none of which exist in this image, and its tests hold no golden matrices.  The oracle is
+pinned to the reference's three known-answer tests, to an autodiff restatement (oracle_ad.py) and
+to the analytic Laplace solution (see tests/test_oracle_pins.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libupdes_oracle.so")
+
+RBF_KINDS = {"polyharmonic": 0, "thin_plate": 1, "gaussian": 2, "multiquadric": 3, "inverse_multiquadric": 4}
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/updes_oracle.c with gcc (recipe: oracle/Makefile)."""
+    src = os.path.join(_HERE, "updes_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "_build/libupdes_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def compute_nb_monomials(max_degree: int, dim: int = 2) -> int:
+    """utils.py:142-144"""
+    return math.comb(max_degree + dim, max_degree)
+
+
+# --------------------------------------------------------------------------------------------
+# Clouds (updes/cloud.py), restated literally with Python dicts and loops: small N only.
+# --------------------------------------------------------------------------------------------
+class _RefCloud:
+    """cloud.py:10-172 (Cloud): bookkeeping + renumbering; support_size is always "max"."""
+
+    def __init__(self, facet_types):
+        self.N = self.Ni = self.Nd = self.Nr = self.Nn = 0
+        self.Np = []
+        self.nodes = {}
+        self.outward_normals = {}
+        self.node_types = {}
+        self.facet_nodes = {}
+        self.dim = 2
+        self.facet_precedence = {k: i for i, (k, v) in enumerate(facet_types.items())}   # cloud.py:40
+        new_facet_types = {}
+        for i, (k, v) in enumerate(facet_types.items()):                                 # cloud.py:43-49
+            new_facet_types[k] = v + str(i) if v[0] == "p" else v
+        self.facet_types = new_facet_types
+
+    def renumber_nodes(self):
+        """cloud.py:115-172: internal, d, n, r, then periodic classes sorted by suffixed type."""
+        i_nodes, d_nodes, n_nodes, r_nodes, p_nodes = [], [], [], [], {}
+        for i in range(self.N):
+            t = self.node_types[i]
+            if t[0] == "i":
+                i_nodes.append(i)
+            elif t[0] == "d":
+                d_nodes.append(i)
+            elif t[0] == "n":
+                n_nodes.append(i)
+            elif t[0] == "r":
+                r_nodes.append(i)
+            elif t[0] == "p":
+                p_nodes[t] = p_nodes.get(t, []) + [i]
+            else:
+                raise ValueError("Unknown node type")
+        all_p = []
+        for k in sorted(p_nodes.keys()):
+            all_p += p_nodes[k]
+        new_numb = {v: k for k, v in enumerate(i_nodes + d_nodes + n_nodes + r_nodes + all_p)}
+        self.node_types = {new_numb[k]: v for k, v in self.node_types.items()}
+        self.nodes = {new_numb[k]: v for k, v in self.nodes.items()}
+        self.facet_nodes = {f: [new_numb[i] for i in ids] for f, ids in self.facet_nodes.items()}
+        self.outward_normals = {new_numb[k]: v for k, v in self.outward_normals.items()}
+        self.renumbering_map = new_numb
+
+    def _sort_dict_by_keys(self, d):
+        """cloud.py:72-81"""
+        items = sorted(d.items(), key=lambda kv: kv[0])
+        return np.stack([np.asarray(v, dtype=np.float64) for _, v in items], axis=0)
+
+    def finalise(self):
+        self.sorted_nodes = self._sort_dict_by_keys(self.nodes)                          # cloud.py:403
+        if len(self.outward_normals) > 0:
+            self.sorted_outward_normals = self._sort_dict_by_keys(self.outward_normals)  # cloud.py:407-408
+        else:
+            self.sorted_outward_normals = np.zeros((0, 2))
+
+
+class RefSquareCloud(_RefCloud):
+    """cloud.py:378-510 (SquareCloud).  Noise uses numpy's generator: the reference's jax.random
+    stream cannot be reproduced without JAX, so noisy clouds are compared on identical arrays."""
+
+    def __init__(self, Nx=7, Ny=5, facet_types=None, noise_seed=None):
+        super().__init__(facet_types)
+        self.Nx, self.Ny, self.N = Nx, Ny, Nx * Ny
+        # cloud.py:411-422
+        self.global_indices = np.zeros((Nx, Ny), dtype=int)
+        self.global_indices_rev = {}
+        count = 0
+        for i in range(Nx):
+            for j in range(Ny):
+                self.global_indices[i, j] = count
+                self.global_indices_rev[count] = (i, j)
+                count += 1
+        # cloud.py:449-488
+        self.facet_nodes = {k: [] for k in self.facet_types}
+        for i in range(self.N):
+            k, l = self.global_indices_rev[i]
+            if l == Ny - 1:
+                self.facet_nodes["North"].append(i); self.node_types[i] = self.facet_types["North"]
+            elif l == 0:
+                self.facet_nodes["South"].append(i); self.node_types[i] = self.facet_types["South"]
+            elif k == Nx - 1:
+                self.facet_nodes["East"].append(i); self.node_types[i] = self.facet_types["East"]
+            elif k == 0:
+                self.facet_nodes["West"].append(i); self.node_types[i] = self.facet_types["West"]
+            else:
+                self.node_types[i] = "i"
+        Np = {v[:-1]: 0 for v in self.facet_types.values() if v[0] == "p"}
+        for f_id, f_type in self.facet_types.items():
+            if f_type == "d":
+                self.Nd += len(self.facet_nodes[f_id])
+            if f_type == "n":
+                self.Nn += len(self.facet_nodes[f_id])
+            if f_type == "r":
+                self.Nr += len(self.facet_nodes[f_id])
+            if f_type[0] == "p":
+                Np[f_type[:-1]] += len(self.facet_nodes[f_id])
+        self.Np = [Np[k] for k in sorted(Np.keys())]
+        self.Ni = self.N - self.Nd - self.Nn - self.Nr - sum(self.Np)
+        # cloud.py:425-446
+        x = np.linspace(0, 1.0, Nx)
+        y = np.linspace(0, 1.0, Ny)
+        rng = np.random.default_rng(noise_seed) if noise_seed is not None else None
+        delta = min(x[1] - x[0], y[1] - y[0]) / 2.0
+        noise_all = rng.uniform(-delta, delta, size=(self.N, 2)) if rng is not None else None
+        for i in range(Nx):
+            for j in range(Ny):
+                gid = int(self.global_indices[i, j])
+                if self.node_types[gid] not in ["d", "n", "r"] and rng is not None:
+                    noise = noise_all[gid]
+                else:
+                    noise = np.zeros(2)
+                self.nodes[gid] = np.array([x[i], y[j]]) + noise
+        # cloud.py:491-510
+        for i in [k for k, v in self.node_types.items() if v[0] in ["n", "r", "p"]]:
+            k, l = self.global_indices_rev[i]
+            if l == Ny - 1:
+                n = np.array([0.0, 1.0])
+            elif l == 0:
+                n = np.array([0.0, -1.0])
+            elif k == Nx - 1:
+                n = np.array([1.0, 0.0])
+            elif k == 0:
+                n = np.array([-1.0, 0.0])
+            self.outward_normals[i] = n
+        self.renumber_nodes()
+        self.finalise()
+
+
+class RefGmshCloud(_RefCloud):
+    """cloud.py:531-734 (GmshCloud) for Gmsh 4.0 ASCII .msh files."""
+
+    def __init__(self, filename, facet_types):
+        super().__init__(facet_types)
+        self.filename = filename
+        self._extract()
+        self._normals()
+        self.renumber_nodes()
+        self.finalise()
+
+    def _extract(self):
+        """cloud.py:578-694"""
+        f = open(self.filename, "r")
+        line = f.readline()
+        while line.find("$PhysicalNames") < 0:
+            line = f.readline()
+        splitline = f.readline().split()
+        names = {}
+        for _ in range(int(splitline[0]) - 1):
+            splitline = f.readline().split()
+            names[int(splitline[1])] = splitline[2][1:-1]
+        self.facet_names = {}
+        while line.find("$Entities") < 0:
+            line = f.readline()
+        splitline = f.readline().split()
+        n_vertices, n_facets = int(splitline[0]), int(splitline[1])
+        for _ in range(n_vertices):
+            f.readline()
+        for _ in range(n_facets):
+            splitline = f.readline().split()
+            self.facet_names[int(splitline[0])] = names[int(splitline[-4])]
+        while line.find("$Nodes") < 0:
+            line = f.readline()
+        splitline = f.readline().split()
+        self.N = int(splitline[1])
+        self.facet_nodes = {v: [] for v in self.facet_names.values()}
+        self.facet_tag_nodes = {k: [] for k in self.facet_names.keys()}
+        corner_membership = {}
+        line = f.readline()
+        while line.find("$EndNodes") < 0:
+            splitline = line.split()
+            entity_id, dim, nb = int(splitline[0]), int(splitline[1]), int(splitline[-1])
+            fnodes = []
+            for _ in range(nb):
+                sl = f.readline().split()
+                node_id = int(sl[0]) - 1
+                self.nodes[node_id] = np.array([float(sl[1]), float(sl[2])])
+                if dim == 0:
+                    corner_membership[node_id] = []
+                elif dim == 1:
+                    self.node_types[node_id] = self.facet_types[self.facet_names[entity_id]]
+                    fnodes.append(node_id)
+                elif dim == 2:
+                    self.node_types[node_id] = "i"
+            if dim == 1:
+                self.facet_nodes[self.facet_names[entity_id]] += fnodes
+                self.facet_tag_nodes[entity_id] += fnodes
+            line = f.readline()
+        while line.find("$Elements") < 0:
+            line = f.readline()
+        f.readline()
+        line = f.readline()
+        while line.find("$EndElements") < 0:
+            splitline = line.split()
+            entity_id, dim, nb = int(splitline[0]), int(splitline[1]), int(splitline[-1])
+            if dim == 1:
+                for _ in range(nb):
+                    ids = [int(t) - 1 for t in f.readline().split()[1:]]
+                    for c in corner_membership.keys():
+                        if c in ids:
+                            for nb_ in ids:
+                                if nb_ != c:
+                                    corner_membership[c].append(entity_id)
+                                    break
+            else:
+                for _ in range(nb):
+                    f.readline()
+            line = f.readline()
+        f.close()
+        for c_id, f_ids in corner_membership.items():
+            chosen = sorted(f_ids, key=lambda t: self.facet_precedence[self.facet_names[t]])[0]
+            name = self.facet_names[chosen]
+            self.node_types[c_id] = self.facet_types[name]
+            self.facet_nodes[name].append(c_id)
+            self.facet_tag_nodes[chosen].append(c_id)
+        self.Ni = sum(1 for v in self.node_types.values() if v[0] == "i")
+        self.Nd = sum(1 for v in self.node_types.values() if v[0] == "d")
+        self.Nr = sum(1 for v in self.node_types.values() if v[0] == "r")
+        self.Nn = sum(1 for v in self.node_types.values() if v[0] == "n")
+
+    def _normals(self):
+        """cloud.py:698-734: +-perpendicular to (nearest same-facet node - node), oriented away
+        from the *second* hit of a k=2 query on the internal nodes (index [0][1], as written)."""
+        from sklearn.neighbors import BallTree
+        in_coords = np.stack([self.nodes[i] for i in range(self.N) if self.node_types[i] == "i"], axis=0)
+        in_tree = BallTree(in_coords, leaf_size=40, metric="euclidean")
+        for f_tag, f_nodes in self.facet_tag_nodes.items():
+            if self.facet_types[self.facet_names[f_tag]][0] in ["n", "r", "p"]:
+                assert len(f_nodes) >= 2
+                f_coords = np.stack([self.nodes[i] for i in f_nodes], axis=0)
+                f_tree = BallTree(f_coords, leaf_size=40, metric="euclidean")
+                for node_id in f_nodes:
+                    cur = self.nodes[node_id]
+                    _, nb = f_tree.query(cur[None], k=2)
+                    closest_f = f_coords[nb[0][1]]
+                    _, nb = in_tree.query(cur[None], k=2)
+                    closest_in = in_coords[nb[0][1]]
+                    invector = closest_in - cur
+                    tangent = closest_f - cur
+                    normal = np.array([-tangent[1], tangent[0]])
+                    if np.dot(normal, invector) > 0:
+                        self.outward_normals[node_id] = -normal / np.linalg.norm(normal)
+                    else:
+                        self.outward_normals[node_id] = normal / np.linalg.norm(normal)
+
+
+# --------------------------------------------------------------------------------------------
+# Matrix blocks (C restatement)
+# --------------------------------------------------------------------------------------------
+def rbf_jet(kind, param, x, center):
+    out = np.zeros(5)
+    lib().uo_rbf_jet(ctypes.c_int(RBF_KINDS[kind]), ctypes.c_double(param), ctypes.c_double(x[0]), ctypes.c_double(x[1]),
+                     ctypes.c_double(center[0]), ctypes.c_double(center[1]), _dp(out))
+    return out
+
+
+def monomial_jet(mid, x):
+    out = np.zeros(5)
+    lib().uo_monomial_jet(ctypes.c_int(mid), ctypes.c_double(x[0]), ctypes.c_double(x[1]), _dp(out))
+    return out
+
+
+def assemble_Phi(cloud, kind, param):
+    """assembly.py:10-36"""
+    nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)
+    N = cloud.N
+    Phi = np.zeros((N, N))
+    lib().uo_assemble_Phi(_dp(nodes), ctypes.c_int(N), ctypes.c_int(RBF_KINDS[kind]), ctypes.c_double(param), _dp(Phi))
+    return Phi
+
+
+def assemble_P(cloud, M):
+    """assembly.py:39-59"""
+    nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)
+    P = np.zeros((cloud.N, M))
+    lib().uo_assemble_P(_dp(nodes), ctypes.c_int(cloud.N), ctypes.c_int(M), _dp(P))
+    return P
+
+
+def assemble_A(cloud, kind, param, M):
+    """assembly.py:62-85"""
+    N = cloud.N
+    A = np.zeros((N + M, N + M))
+    A[:N, :N] = assemble_Phi(cloud, kind, param)
+    P = assemble_P(cloud, M)
+    A[:N, N:] = P
+    A[N:, :N] = P.T
+    return A
+
+
+def assemble_op_Phi_P(cloud, kind, param, M, rowcoef):
+    """assembly.py:93-137 with the operator given in lowered form (Ni x 5 coefficients)."""
+    nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)
+    rowcoef = np.ascontiguousarray(rowcoef, dtype=np.float64)
+    assert rowcoef.shape == (cloud.Ni, 5)
+    opPhi = np.zeros((cloud.Ni, cloud.N))
+    opP = np.zeros((cloud.Ni, M))
+    lib().uo_assemble_op_Phi_P(_dp(nodes), ctypes.c_int(cloud.N), ctypes.c_int(cloud.Ni), ctypes.c_int(M),
+                               ctypes.c_int(RBF_KINDS[kind]), ctypes.c_double(param), _dp(rowcoef), _dp(opPhi), _dp(opP))
+    return opPhi, opP
+
+
+def assemble_bd_Phi_P(cloud, kind, param, M, betas=None):
+    """assembly.py:141-362"""
+    nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)
+    Np = np.asarray(cloud.Np, dtype=np.int32)
+    Nb = cloud.Nd + cloud.Nn + cloud.Nr + int(Np.sum())
+    normals = np.ascontiguousarray(cloud.sorted_outward_normals, dtype=np.float64)
+    if normals.size == 0:
+        normals = np.zeros((1, 2))
+    if betas is None:
+        betas = np.zeros(max(cloud.Nr, 1))
+    betas = np.ascontiguousarray(betas, dtype=np.float64)
+    bdPhi = np.zeros((Nb, cloud.N))
+    bdP = np.zeros((Nb, M))
+    lib().uo_assemble_bd_Phi_P(_dp(nodes), ctypes.c_int(cloud.N), ctypes.c_int(cloud.Ni), ctypes.c_int(cloud.Nd),
+                               ctypes.c_int(cloud.Nn), ctypes.c_int(cloud.Nr), _ip(Np), ctypes.c_int(len(Np)),
+                               _dp(normals), _dp(betas), ctypes.c_int(M), ctypes.c_int(RBF_KINDS[kind]),
+                               ctypes.c_double(param), _dp(bdPhi), _dp(bdP))
+    return bdPhi, bdP
+
+
+def assemble_diffMat(cloud, kind, param, M, rowcoef, betas=None):
+    """assembly.py:384-396: diffMat = [[opPhi, opP], [bdPhi, bdP]], N x (N+M)."""
+    opPhi, opP = assemble_op_Phi_P(cloud, kind, param, M, rowcoef)
+    bdPhi, bdP = assemble_bd_Phi_P(cloud, kind, param, M, betas)
+    return np.concatenate([np.concatenate([opPhi, opP], axis=1), np.concatenate([bdPhi, bdP], axis=1)], axis=0)
+
+
+def assemble_K(cloud, kind, param, M, rowcoef, betas=None):
+    """The (N+M)^2 collocation system the product factorises:
+    K = [[opPhi, opP], [bdPhi, bdP], [P^T, 0]] -- composed from the reference's own blocks."""
+    N = cloud.N
+    K = np.zeros((N + M, N + M))
+    K[:N, :] = assemble_diffMat(cloud, kind, param, M, rowcoef, betas)
+    K[N:, :N] = assemble_P(cloud, M).T
+    return K
+
+
+def eval_field(xs, centers, coeffs, kind, param, which):
+    """operators.py:118-147 / :156-184 / :294-330.  which: 'value', 'dx', 'dy', 'laplacian'."""
+    code = {"value": 0, "dx": 1, "dy": 2, "laplacian": 3}[which]
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    centers = np.ascontiguousarray(centers, dtype=np.float64)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    N = centers.shape[0]
+    M = coeffs.shape[0] - N
+    out = np.zeros(xs.shape[0])
+    lib().uo_eval_field(_dp(xs), ctypes.c_int(xs.shape[0]), _dp(centers), ctypes.c_int(N), ctypes.c_int(M),
+                        _dp(coeffs), ctypes.c_int(RBF_KINDS[kind]), ctypes.c_double(param), ctypes.c_int(code), _dp(out))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Right-hand side and the reference formulation of the solve
+# --------------------------------------------------------------------------------------------
+def assemble_q(cloud, q_internal, boundary_arrays):
+    """assembly.py:434-485: q[:Ni] = rhs operator on internal nodes; facet nodes get the BC array."""
+    q = np.zeros(cloud.N)
+    q[:cloud.Ni] = q_internal
+    for f_id in cloud.facet_types.keys():
+        assert f_id in boundary_arrays, "facets and boundary functions don't match ids"
+        q[np.asarray(cloud.facet_nodes[f_id], dtype=int)] = boundary_arrays[f_id]
+    return q
+
+
+def reference_solve(cloud, kind, param, max_degree, rowcoef, q, betas=None):
+    """The reference's linear algebra, literally (assembly.py:366-410, operators.py:602-616):
+    B = (diffMat @ inv(A))[:, :N];  u = QR-solve(B, q);  coeffs = inv(A) @ [u; 0].
+    Returns (vals, coeffs, B)."""
+    import scipy.linalg as sla
+    N = cloud.N
+    M = compute_nb_monomials(max_degree, 2)
+    D = assemble_diffMat(cloud, kind, param, M, rowcoef, betas)
+    A = assemble_A(cloud, kind, param, M)
+    inv_A = np.linalg.inv(A)                      # assembly.py:90
+    B = (D @ inv_A)[:, :N]                        # assembly.py:399-401
+    Q, R = sla.qr(B)                              # operators.py:612-613 (lineax QR)
+    u = sla.solve_triangular(R, Q.T @ q)
+    coeffs = inv_A @ np.concatenate([u, np.zeros(M)])   # assembly.py:404-410
+    return u, coeffs, B

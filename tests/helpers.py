@@ -1,0 +1,32 @@
+"""Shared test helpers: reference-style problem definitions used by CPU and GPU tests."""
+import numpy as np
+
+import updes_b200 as u
+
+CONFIG1_FACETS = {"South": "n", "West": "d", "North": "d", "East": "d"}          # README example
+CONFIG2_FACETS = {"South": "p1", "North": "p1", "West": "p2", "East": "p2"}      # demos/Advection/01
+
+
+def rel_err_rowscaled(got, want):
+    """|got - want| / max(|want|, rowscale): the 1e-12 'relative per entry' test with the absolute
+    floor SURVEY.md section 7 (hard part 4) asks for -- entries that pass through zero have no
+    meaningful relative error, so the floor is the largest magnitude in the row."""
+    got = np.asarray(got); want = np.asarray(want)
+    scale = np.maximum(np.abs(want), np.max(np.abs(want), axis=-1, keepdims=True))
+    scale = np.where(scale == 0, 1.0, scale)
+    return np.max(np.abs(got - want) / scale)
+
+
+def laplace_op(lib):
+    def op(x, center, rbf, monomial, fields):
+        return lib.nodal_laplacian(x, center, rbf, monomial)
+    return op
+
+
+def advdiff_op(lib, dt=1e-4, vel=(100.0, 0.0), k=0.08, dot=np.dot):
+    def op(x, center, rbf, monomial, fields):
+        val = lib.nodal_value(x, center, rbf, monomial)
+        grad = lib.nodal_gradient(x, center, rbf, monomial)
+        lap = lib.nodal_laplacian(x, center, rbf, monomial)
+        return (val / dt) + dot(np.asarray(vel), grad) - k * lap
+    return op

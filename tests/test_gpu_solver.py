@@ -1,0 +1,76 @@
+"""GPU parity of the whole path: pde_solver vs the reference formulation (inv + GEMM + QR) on the CPU."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+import updes_b200 as u
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, laplace_op
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+def test_readme_laplace_matches_reference_formulation(oracle):
+    """README example (config 1): 30x20, polyharmonic a=1, degree 1, Dirichlet sine / Neumann."""
+    cloud = u.SquareCloud(Nx=30, Ny=20, facet_types=CONFIG1_FACETS)
+    sine = lambda c: np.sin(np.pi * c[0])
+    zero = lambda c: 0.0
+    bcs = {"South": zero, "West": zero, "North": sine, "East": zero}
+    sol = u.pde_solver_jit(diff_operator=laplace_op(u), rhs_operator=lambda x, centers, rbf, fields: 0.0, cloud=cloud,
+                           boundary_conditions=bcs, rbf=u.polyharmonic, max_degree=1)
+    bc_arr = u.boundary_conditions_func_to_arr(bcs, cloud)
+    q = oracle.assemble_q(cloud, np.zeros(cloud.Ni), bc_arr)
+    coef = np.tile([0.0, 0.0, 0.0, 1.0, 1.0], (cloud.Ni, 1))
+    vals, coeffs, B = oracle.reference_solve(cloud, "polyharmonic", 1, 1, coef, q)
+    assert _rel(sol.vals, vals) <= 1e-8                   # north_star: solutions within 1e-8 relative
+    # analytic solution of demos/Laplace/00_laplace_with_rbf.py:109-110
+    xy = cloud.sorted_nodes
+    exact = np.sin(np.pi * xy[:, 0]) * np.cosh(np.pi * xy[:, 1]) / np.cosh(np.pi)
+    assert np.max(np.abs(sol.vals - exact)) <= 2e-2
+    # SteadySol.mat is the reference's B (assembly.py:396-401)
+    assert _rel(sol.mat, B) <= 1e-6
+
+
+def test_advection_periodic_time_steps(oracle):
+    """Config 2: periodic adv-diff, factor once, several solves with rhs = value(u)/DT."""
+    DT = 1e-4
+    cloud = u.SquareCloud(Nx=35, Ny=35, facet_types=CONFIG2_FACETS, noise_key=11)
+    rbf = partial(u.polyharmonic, a=1)
+    xy = cloud.sorted_nodes
+    u0 = np.exp(-((xy[:, 0] - 0.35) ** 2 + (xy[:, 1] - 0.5) ** 2) / (2 * 0.1 ** 2))
+    zero = lambda c: 0.0
+    bcs = {k: zero for k in CONFIG2_FACETS}
+    rhs = lambda x, centers, rbf, fields: u.value(x, fields[:, 0], centers, rbf) / DT
+    coef = np.tile([1 / DT, 100.0, 0.0, -0.08, -0.08], (cloud.Ni, 1))
+    uu, ref = u0.copy(), u0.copy()
+    launches0 = None
+    for step in range(3):
+        sol = u.pde_solver_jit(diff_operator=advdiff_op(u, DT), rhs_operator=rhs, rhs_args=[uu], cloud=cloud,
+                               boundary_conditions=bcs, rbf=rbf, max_degree=0)
+        uu = sol.vals
+        # reference formulation on the CPU: coefficients of the previous field, value(x)/DT on internal nodes
+        A = oracle.assemble_A(cloud, "polyharmonic", 1, 1)
+        cprev = np.linalg.solve(A, np.concatenate([ref, np.zeros(1)]))
+        q_int = oracle.eval_field(cloud.sorted_nodes[:cloud.Ni], cloud.sorted_nodes, cprev, "polyharmonic", 1, "value") / DT
+        q = oracle.assemble_q(cloud, q_int, {k: np.zeros(len(cloud.facet_nodes[k])) for k in cloud.facet_types})
+        ref, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 0, coef, q)
+        assert _rel(uu, ref) <= 1e-6, (step, _rel(uu, ref))
+
+
+def test_gaussian_constant_field_gmsh_like(oracle):
+    """Reference test_operators.py restated on a square cloud: all-Neumann, diff = nodal_value,
+    rhs = 12 -> constant field; its gradient and divergence vanish (atol 1e-2 in the reference)."""
+    cloud = u.SquareCloud(Nx=22, Ny=22, facet_types={k: "n" for k in ("South", "West", "North", "East")}, noise_key=12)
+    rbf = partial(u.gaussian, eps=10.0)
+    op = lambda x, c, r, m, f: u.nodal_value(x, c, r, m)
+    sol = u.pde_solver(op, lambda x, centers, rbf, fields: 12.0, cloud, {k: (lambda c: 0.0) for k in cloud.facet_types},
+                       rbf, 1)
+    g = u.gradient_vec(cloud.sorted_nodes, sol.coeffs, cloud.sorted_nodes, rbf)
+    d = u.divergence_vec(cloud.sorted_nodes, np.stack([sol.coeffs, sol.coeffs], -1), cloud.sorted_nodes, rbf)
+    assert np.allclose(np.linalg.norm(g, axis=-1)[:cloud.Ni], 0, atol=1e-2)
+    assert np.allclose(d[:cloud.Ni], 0, atol=1e-2)
+    assert np.allclose(sol.vals[:cloud.Ni], 12.0, atol=1e-6)

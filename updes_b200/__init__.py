@@ -1,0 +1,18 @@
+"""updes_b200 -- B200-native global RBF-collocation hot path of ddrous/Updes.
+
+Drop-in for the path  pde_solver / pde_solver_jit  over a SquareCloud or GmshCloud with the built-in
+kernels, max_degree polynomial augmentation and Dirichlet / Neumann / Robin / periodic facets
+(reference: updes/operators.py:559-683, updes/assembly.py).  Compute runs in hand-written CUDA for
+sm_100a behind the C-ABI of include/updes_b200.h; there is no CPU fallback.
+"""
+from .cloud import Cloud, GmshCloud, SquareCloud
+from .rbf import (compute_nb_monomials, distance, gaussian, identify_rbf, inverse_multiquadric, make_all_monomials,
+                  make_monomial, multiquadric, polyharmonic, thin_plate)
+from .operators import (BatchPoints, OperatorLoweringError, SteadySol, boundary_conditions_func_to_arr, clear_cache,
+                        compute_coefficients, core_compute_coefficients, divergence, divergence_vec, dot,
+                        duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vec, laplacian,
+                        laplacian_vec, lower_diff_operator, nodal_div_grad, nodal_gradient, nodal_laplacian,
+                        nodal_value, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
+                        zerofy_periodic_cond)
+
+__version__ = "0.1.0"

@@ -1,0 +1,83 @@
+"""ctypes binding of the C-ABI in ``include/updes_b200.h`` (``libupdes_b200.so``, built in-tree).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present, every
+compute entry point raises.  Device memory and streams come from PyTorch (plumbing only).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libupdes_b200.so")
+
+c_double_p = ctypes.c_void_p
+c_int32_p = ctypes.c_void_p
+
+
+class UpdesRows(ctypes.Structure):
+    """struct UpdesRows (include/updes_b200.h): device pointers of the row descriptors."""
+    _fields_ = [("pts", ctypes.c_void_p), ("p1", ctypes.c_void_p), ("p2", ctypes.c_void_p),
+                ("cphi1", ctypes.c_void_p), ("cphi2", ctypes.c_void_p), ("cpol1", ctypes.c_void_p),
+                ("cpol2", ctypes.c_void_p), ("skip", ctypes.c_void_p)]
+
+
+# name -> (restype, argtypes): every symbol the header declares
+_I64, _I32, _VP, _DBL = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_double
+SIGNATURES = {
+    "updes_assemble_rows": (_I32, [_I32, _DBL, _I32, _I32, _VP, ctypes.POINTER(UpdesRows), _I64, _I64, _I32, _VP, _I64, _VP]),
+    "updes_assemble_block": (_I32, [_I32, _DBL, _I32, _I32, _VP, ctypes.POINTER(UpdesRows), _I64, _I64, _I64, _I64, _I32, _VP, _I64, _VP]),
+    "updes_eval_jets_workspace_bytes": (ctypes.c_size_t, [_I32, _I32, _I32]),
+    "updes_eval_jets": (_I32, [_I32, _DBL, _I32, _I32, _VP, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "updes_lu_create": (_I32, [ctypes.POINTER(_VP), _I64, _I64]),
+    "updes_lu_destroy": (_I32, [_VP]),
+    "updes_lu_factor": (_I32, [_VP, _VP, _VP, _VP, _VP]),
+    "updes_lu_solve": (_I32, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
+    "updes_dgemm_sub": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
+    "updes_lu_panel": (_I32, [_VP, _VP, _I64, _I64, _VP, _VP, _VP]),
+    "updes_b200_version": (ctypes.c_char_p, []),
+    "updes_launch_count": (_I64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed for loading; needed for any call that computes)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "updes_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C updes_b200/csrc`).  There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise ValueError("updes_b200.%s: bad argument #%d" % (what, -rc))
+    raise RuntimeError("updes_b200.%s: CUDA error %d while enqueuing" % (what, rc))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("updes_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().updes_launch_count())

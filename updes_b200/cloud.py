@@ -1,0 +1,276 @@
+"""Clouds of collocation nodes: the input contract of the hot path.
+
+Re-statement of ``updes/cloud.py`` (reference) for the *global* path (``support_size="max"``), in
+vectorised numpy: O(N) work and memory, no ``(N, N-1)`` support table (reference cloud.py:108-112
+materialises one, 64.8 GB at N = 90 000).  What the assembly consumes is reproduced exactly:
+
+* ``sorted_nodes`` (N, 2), renumbered internal -> dirichlet -> neumann -> robin -> periodic classes
+  sorted by suffixed type, ascending original id inside each class      (cloud.py:115-172)
+* ``sorted_outward_normals`` for n / r / p nodes, indexed ``[i - Ni - Nd]`` (cloud.py:407-408)
+* counts ``N, Ni, Nd, Nn, Nr, Np`` (list per periodic group), ``facet_nodes``, ``facet_types`` with the
+  facet index appended to periodic types (cloud.py:43-49), ``renumbering_map``.
+
+``SquareCloud``  : cloud.py:378-510.     ``GmshCloud`` : cloud.py:531-734 (Gmsh 4.0 ASCII reader).
+Every node's support is "all other nodes" (cloud.py:110-112 drops the node itself), which the
+assembly encodes as a skipped diagonal entry rather than an index table.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+class Cloud:
+    """Base bookkeeping shared by all clouds (reference cloud.py:10-50)."""
+
+    def __init__(self, facet_types, support_size="max"):
+        if support_size not in ("max", None):
+            raise NotImplementedError(
+                "updes_b200 implements the global collocation path only (support_size='max'); "
+                "local RBF-FD supports are out of scope (reference README lists them as ill-conditioned)")
+        self.support_size = "max"
+        self.N = self.Ni = self.Nd = self.Nr = self.Nn = 0
+        self.Np = []
+        self.dim = 2
+        self.facet_precedence = {k: i for i, (k, v) in enumerate(facet_types.items())}
+        self.facet_types = {k: (v + str(i) if v[0] == "p" else v) for i, (k, v) in enumerate(facet_types.items())}
+        self.facet_nodes = {}
+        self.node_types = {}
+        self.outward_normals = {}
+        self.renumbering_map = {}
+
+    # -- renumbering (cloud.py:115-172) -----------------------------------------------------------
+    def _renumber(self, types, coords, normals_by_old, facet_nodes_old):
+        """types: array of str per original id; returns the sorted arrays and fills the dicts."""
+        N = len(types)
+        first = np.array([t[0] for t in types])
+        order = [np.flatnonzero(first == c) for c in ("i", "d", "n", "r")]
+        p_ids = np.flatnonzero(first == "p")
+        for key in sorted(set(types[p_ids])):
+            order.append(np.flatnonzero(types == key))
+        old_of_new = np.concatenate(order) if N else np.zeros(0, dtype=int)
+        if len(old_of_new) != N:
+            raise ValueError("Unknown node type")
+        new_of_old = np.empty(N, dtype=np.int64)
+        new_of_old[old_of_new] = np.arange(N)
+        self._new_of_old = new_of_old
+        self._old_of_new = old_of_new
+        self.renumbering_map = dict(zip(range(N), new_of_old.tolist()))
+        self.sorted_nodes = np.ascontiguousarray(coords[old_of_new], dtype=np.float64)
+        sorted_types = types[old_of_new]
+        self.node_types = dict(zip(range(N), sorted_types.tolist()))
+        self.facet_nodes = {f: new_of_old[np.asarray(ids, dtype=np.int64)].tolist() for f, ids in facet_nodes_old.items()}
+        # normals exist for n / r / p nodes, which are contiguous after the Dirichlet block
+        nb = self.Nn + self.Nr + sum(self.Np)
+        start = self.Ni + self.Nd
+        if nb > 0:
+            son = np.zeros((nb, 2))
+            for old, nv in normals_by_old.items():
+                son[new_of_old[old] - start] = nv
+            self.sorted_outward_normals = son
+            self.outward_normals = {start + k: son[k] for k in range(nb)}
+        else:
+            self.sorted_outward_normals = np.zeros((0, 2))
+            self.outward_normals = {}
+
+    @property
+    def nodes(self):
+        """dict new id -> coordinates (reference attribute ``Cloud.nodes`` after renumbering)."""
+        return {i: self.sorted_nodes[i] for i in range(self.N)}
+
+    def sort_dict_by_keys(self, dictionary):
+        """cloud.py:72-81"""
+        items = sorted(dictionary.items(), key=lambda kv: kv[0])
+        return np.stack([np.asarray(v) for _, v in items], axis=0)
+
+
+class SquareCloud(Cloud):
+    """Regular or jittered grid on the unit square (reference cloud.py:378-510).
+
+    ``noise_key``: ``None`` for the regular grid, else an integer seed (or array whose entries are
+    folded into one).  The reference draws the jitter from ``jax.random``; that stream cannot be
+    reproduced without JAX, so jittered clouds use ``numpy.random.default_rng(seed)`` -- the rule is
+    the same: uniform in +-min(dx, dy)/2 on every node that is not d / n / r (cloud.py:431-444).
+    """
+
+    def __init__(self, Nx=7, Ny=5, noise_key=None, **kwargs):
+        super().__init__(**kwargs)
+        for k in self.facet_types:
+            if k not in ("North", "South", "East", "West"):
+                raise KeyError("SquareCloud facets must be named North, South, East, West (cloud.py:455-468)")
+        self.Nx, self.Ny, self.N = Nx, Ny, Nx * Ny
+        gid = np.arange(self.N)
+        I, J = gid // Ny, gid % Ny                       # cloud.py:411-422: gid = i*Ny + j
+        self.global_indices = gid.reshape(Nx, Ny)
+        self.global_indices_rev = None                   # built lazily (dict of N tuples)
+
+        # node types with the reference's facet precedence N, S, E, W (cloud.py:455-468)
+        facet_of = np.full(self.N, "", dtype=object)
+        facet_of[I == 0] = "West"
+        facet_of[I == Nx - 1] = "East"
+        facet_of[J == 0] = "South"
+        facet_of[J == Ny - 1] = "North"
+        types = np.full(self.N, "i", dtype=object)
+        facet_nodes_old = {k: [] for k in self.facet_types}
+        for f in ("West", "East", "South", "North"):
+            ids = np.flatnonzero(facet_of == f)
+            if len(ids):
+                types[ids] = self.facet_types[f]
+                facet_nodes_old[f] = ids
+        # counts (cloud.py:470-488)
+        Np = {v[:-1]: 0 for v in self.facet_types.values() if v[0] == "p"}
+        for f, t in self.facet_types.items():
+            cnt = len(facet_nodes_old[f])
+            if t == "d":
+                self.Nd += cnt
+            elif t == "n":
+                self.Nn += cnt
+            elif t == "r":
+                self.Nr += cnt
+            elif t[0] == "p":
+                Np[t[:-1]] += cnt
+        self.Np = [Np[k] for k in sorted(Np)]
+        self.Ni = self.N - self.Nd - self.Nn - self.Nr - sum(self.Np)
+
+        # coordinates (cloud.py:425-446)
+        x = np.linspace(0, 1.0, Nx)
+        y = np.linspace(0, 1.0, Ny)
+        coords = np.stack([x[I], y[J]], axis=1)
+        if noise_key is not None:
+            seed = int(np.asarray(noise_key).astype(np.int64).ravel().sum()) if not isinstance(noise_key, (int, np.integer)) else int(noise_key)
+            delta = min(x[1] - x[0], y[1] - y[0]) / 2.0
+            noise = np.random.default_rng(seed).uniform(-delta, delta, size=(self.N, 2))
+            movable = ~np.isin(types, ["d", "n", "r"])
+            coords = coords + noise * movable[:, None]
+
+        # outward normals of n / r / p nodes, same precedence (cloud.py:491-510)
+        normals = {}
+        first = np.array([t[0] for t in types])
+        table = {"North": (0.0, 1.0), "South": (0.0, -1.0), "East": (1.0, 0.0), "West": (-1.0, 0.0)}
+        for f, nv in table.items():
+            for old in np.flatnonzero((facet_of == f) & np.isin(first, ["n", "r", "p"])):
+                normals[int(old)] = np.array(nv)
+        self._renumber(types, coords, normals, facet_nodes_old)
+
+
+class GmshCloud(Cloud):
+    """Cloud read from a Gmsh 4.0 ASCII ``.msh`` file (reference cloud.py:531-734).
+
+    Only ``.msh`` input is supported: generating a mesh from a ``.py`` script needs the ``gmsh``
+    package (cloud.py:573-575), which is outside the hot path.  Periodic facets are not available
+    on Gmsh clouds in the reference either (``Np`` is never set, cloud.py:690-694).
+    """
+
+    def __init__(self, filename, mesh_save_location=None, **kwargs):
+        super().__init__(**kwargs)
+        if not str(filename).endswith(".msh"):
+            raise NotImplementedError("GmshCloud reads .msh files; run gmsh yourself to produce one")
+        self.filename = filename
+        types, coords, facet_nodes_old, tag_nodes = self._read_msh()
+        normals = self._normals(types, coords, tag_nodes)
+        self._renumber(types, coords, normals, facet_nodes_old)
+        self.facet_tag_nodes = {t: self._new_of_old[np.asarray(ids, dtype=np.int64)].tolist() for t, ids in tag_nodes.items()}
+
+    @staticmethod
+    def _section(lines, name):
+        start = next(i for i, l in enumerate(lines) if l.strip() == "$" + name)
+        end = next(i for i in range(start, len(lines)) if lines[i].strip() == "$End" + name)
+        return lines[start + 1:end]
+
+    def _read_msh(self):
+        with open(self.filename, "r") as f:
+            lines = f.read().splitlines()
+        # physical names: all but the last one are facets (cloud.py:586-593)
+        sec = self._section(lines, "PhysicalNames")
+        phys = {}
+        for l in sec[1:int(sec[0].split()[0])]:
+            t = l.split()
+            phys[int(t[1])] = t[2][1:-1]
+        # curve entity -> physical name (cloud.py:596-605)
+        sec = self._section(lines, "Entities")
+        h = sec[0].split()
+        n_points, n_curves = int(h[0]), int(h[1])
+        self.facet_names = {}
+        for l in sec[1 + n_points:1 + n_points + n_curves]:
+            t = l.split()
+            self.facet_names[int(t[0])] = phys[int(t[-4])]
+        # nodes (cloud.py:608-648)
+        sec = self._section(lines, "Nodes")
+        self.N = int(sec[0].split()[1])
+        coords = np.zeros((self.N, 2))
+        types = np.full(self.N, "", dtype=object)
+        facet_nodes_old = {v: [] for v in self.facet_names.values()}
+        tag_nodes = {k: [] for k in self.facet_names}
+        corners = {}
+        k = 1
+        while k < len(sec):
+            t = sec[k].split()
+            ent, dim, nb = int(t[0]), int(t[1]), int(t[-1])
+            block = []
+            for l in sec[k + 1:k + 1 + nb]:
+                u = l.split()
+                nid = int(u[0]) - 1
+                coords[nid] = (float(u[1]), float(u[2]))
+                if dim == 0:
+                    corners[nid] = []
+                elif dim == 1:
+                    types[nid] = self.facet_types[self.facet_names[ent]]
+                    block.append(nid)
+                elif dim == 2:
+                    types[nid] = "i"
+            if dim == 1:
+                facet_nodes_old[self.facet_names[ent]] += block
+                tag_nodes[ent] += block
+            k += 1 + nb
+        # line elements decide which facets a corner touches (cloud.py:651-674)
+        sec = self._section(lines, "Elements")
+        k = 1
+        while k < len(sec):
+            t = sec[k].split()
+            ent, dim, nb = int(t[0]), int(t[1]), int(t[-1])
+            if dim == 1:
+                for l in sec[k + 1:k + 1 + nb]:
+                    ids = [int(v) - 1 for v in l.split()[1:]]
+                    for c in corners:
+                        if c in ids and any(v != c for v in ids):
+                            corners[c].append(ent)
+            k += 1 + nb
+        # corner goes to the facet listed first in the user's facet_types (cloud.py:680-688)
+        for c, ents in corners.items():
+            chosen = sorted(ents, key=lambda e: self.facet_precedence[self.facet_names[e]])[0]
+            name = self.facet_names[chosen]
+            types[c] = self.facet_types[name]
+            facet_nodes_old[name].append(c)
+            tag_nodes[chosen].append(c)
+        first = np.array([t[0] for t in types])
+        self.Ni = int(np.sum(first == "i"))
+        self.Nd = int(np.sum(first == "d"))
+        self.Nr = int(np.sum(first == "r"))
+        self.Nn = int(np.sum(first == "n"))
+        return types, coords, facet_nodes_old, tag_nodes
+
+    def _normals(self, types, coords, tag_nodes):
+        """Approximate outward normals (cloud.py:698-734): perpendicular to the chord towards the
+        nearest node of the same curve, flipped away from the *second* hit of a k=2 query among the
+        internal nodes (the reference indexes ``neighbours[0][1]``)."""
+        from sklearn.neighbors import BallTree
+        normals = {}
+        in_coords = coords[np.array([t == "i" for t in types])]
+        in_tree = BallTree(in_coords, leaf_size=40, metric="euclidean")
+        for tag, ids in tag_nodes.items():
+            if self.facet_types[self.facet_names[tag]][0] not in ("n", "r", "p"):
+                continue
+            assert len(ids) >= 2, " Mesh not fine enough for normal computation "
+            f_coords = coords[np.asarray(ids)]
+            f_tree = BallTree(f_coords, leaf_size=40, metric="euclidean")
+            _, nb_f = f_tree.query(f_coords, k=2)
+            _, nb_i = in_tree.query(f_coords, k=2)
+            for row, nid in enumerate(ids):
+                cur = coords[nid]
+                tangent = f_coords[nb_f[row][1]] - cur
+                invector = in_coords[nb_i[row][1]] - cur
+                normal = np.array([-tangent[1], tangent[0]])
+                nrm = np.linalg.norm(normal)
+                normals[int(nid)] = -normal / nrm if np.dot(normal, invector) > 0 else normal / nrm
+        return normals

@@ -1,0 +1,330 @@
+// FP64 trailing update of the blocked LU:  C -= A * B  on sub-blocks of one row-major matrix.
+//
+// This is the only dense contraction on the path (the reference reaches it through
+// jnp.linalg.inv + `diffMat @ inv_A`, updes/assembly.py:90,:399, and lineax QR, operators.py:612).
+// Blackwell's tcgen05 has no FP64 kind, so the contraction runs on the legacy FP64 tensor path:
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), measured 37.0 TFLOP/s raw on B200 (profiles/r01_ceilings.json).
+//
+// Structure (one persistent CTA per SM, static tile schedule):
+//   * thread 0 doubles as the producer: it issues TMA (cp.async.bulk.tensor) loads of the
+//     A tile (128 rows x 16 k) and the B tile (16 k x BN cols) STAGES-1 k-tiles ahead into a
+//     shared-memory ring guarded by full/empty mbarriers;
+//   * all 8 warps are consumers: each owns a (128/WARPS_M) x 32 accumulator tile in registers and
+//     issues DMMAs from shared-memory fragments; the epilogue subtracts from C in place.
+// Shared-memory layout: both operands use the 128-byte TMA swizzle.  An A row is 16 doubles
+// (128 B); the fragment row order inside each 8-row group is permuted (0,4,1,5,2,6,3,7) and the
+// two DMMAs of a k-pair take the even / odd k of each 16-byte chunk, which makes every
+// LDS.128 (A) and LDS.64 (B) bank-conflict-free (derivation in DESIGN.md).
+#include "lu.cuh"
+#include <mutex>
+
+namespace updes {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_CONSUMERS = 8;
+constexpr int GEMM_THREADS = GEMM_CONSUMERS * 32;
+
+struct GemmParams {
+  double *C;           // matrix base
+  long long ld;
+  long long rc, cc;    // C block origin
+  long long ra, ca;    // A block origin (m x k)
+  long long rb, cb;    // B block origin (k x n)
+  long long m, n, k;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Tile order: groups of GROUP_M row-tiles swept across all column-tiles, so one wave of CTAs
+// touches ~GROUP_M A strips and ~num_sms/GROUP_M B strips (L2 reuse) instead of num_sms A strips.
+constexpr int GEMM_GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(long long t, int tiles_m, int tiles_n, int &mt, int &nt) {
+  const long long per_group = (long long)GEMM_GROUP_M * tiles_n;
+  const int group = (int)(t / per_group);
+  const int first_m = group * GEMM_GROUP_M;
+  const int gsz = min(GEMM_GROUP_M, tiles_m - first_m);
+  const int rem = (int)(t - (long long)group * per_group);
+  mt = first_m + rem % gsz;
+  nt = rem / gsz;
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int WARPS_N = BN / 32;
+  static constexpr int WARPS_M = GEMM_CONSUMERS / WARPS_N;
+  static constexpr int WM = GEMM_BM / WARPS_M;     // rows per warp
+  static constexpr int MI = WM / 8;                // 8-row fragments per warp
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 8;
+  static constexpr int B_BYTES = BN * GEMM_BK * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 128 ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmParams P) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; s++) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (Cfg::STAGES + s), GEMM_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int tiles_m = (int)((P.m + GEMM_BM - 1) / GEMM_BM);
+  const int tiles_n = (int)((P.n + BN - 1) / BN);
+  const long long ntiles = (long long)tiles_m * tiles_n;
+  const int ktiles = (int)(P.k / GEMM_BK);
+
+  // ------------------------------ producer state (thread 0) ------------------------------
+  // No dedicated producer warp: a 9th warp would round the CTA up to 12 warps of register
+  // allocation (168 regs/thread) and spill the 128 accumulator registers.  Thread 0 issues the TMA
+  // loads STAGES-1 k-tiles ahead of the consumers, all 8 warps (255 regs) do the math.
+  long long p_t = blockIdx.x;
+  int p_kt = 0, p_stage = 0;
+  uint32_t p_phase = 0;
+  auto produce_one = [&]() {
+    if (p_t >= ntiles) return;
+    int mt, nt;
+    tile_coords(p_t, tiles_m, tiles_n, mt, nt);
+    const int arow = (int)(P.ra + (long long)mt * GEMM_BM);
+    const int bcol = (int)(P.cb + (long long)nt * BN);
+    mbar_wait(bars + 8 * (Cfg::STAGES + p_stage), p_phase ^ 1);
+    const uint32_t full = bars + 8 * p_stage;
+    mbar_expect_tx(full, Cfg::STAGE_BYTES);
+    const uint32_t sa = smem_base + p_stage * Cfg::STAGE_BYTES;
+    tma_load_2d(sa, &mapA, (int)(P.ca + p_kt * GEMM_BK), arow, full);
+#pragma unroll
+    for (int g = 0; g < BN / 16; g++)
+      tma_load_2d(sa + Cfg::A_BYTES + g * 2048, &mapB, bcol + 16 * g, (int)(P.rb + p_kt * GEMM_BK), full);
+    if (++p_stage == Cfg::STAGES) { p_stage = 0; p_phase ^= 1; }
+    if (++p_kt == ktiles) { p_kt = 0; p_t += gridDim.x; }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int i = 0; i < Cfg::STAGES - 1; i++) produce_one();
+  }
+
+  // ------------------------------ consumers ------------------------------
+  const int warp_m = warp % Cfg::WARPS_M, warp_n = warp / Cfg::WARPS_M;
+  const int fr = lane >> 2, s4 = lane & 3;
+  const int prow = (fr >> 1) | ((fr & 1) << 2);                 // permuted row inside an 8-row group
+  // A: byte offset of (row = warp_m*WM + i*8 + prow, chunk) inside the stage = row*128 + ((4h+s4)^prow)*16
+  const uint32_t a_row_off = (uint32_t)(warp_m * Cfg::WM + prow) * 128u;
+  const uint32_t a_ch0 = (uint32_t)((s4 ^ prow) << 4), a_ch1 = (uint32_t)(((4 + s4) ^ prow) << 4);
+  // B: element (k = 8h + 2 s4 + p, n = warp_n*32 + jn*8 + fr) lives at
+  //    (n>>4)*2048 + k*128 + (((n&15)>>1) ^ (k&7))*16 + (n&1)*8.
+  // With n&15 = (jn&1)*8 + fr the chunk index is ((fr>>1) ^ k7) ^ ((jn&1)<<2), so the four jn
+  // offsets are  (base_p ^ ((jn&1)<<6)) + (jn>>1)*2048 : two base registers per parity p.
+  uint32_t b_base[2][2];
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    const int k7 = 2 * s4 + p;
+    const uint32_t base = (uint32_t)(warp_n * 2 * 2048 + k7 * 128 + ((((fr >> 1) ^ k7)) << 4) + (fr & 1) * 8);
+    b_base[p][0] = base;
+    b_base[p][1] = base ^ 64u;
+  }
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int mt, nt;
+    tile_coords(t, tiles_m, tiles_n, mt, nt);
+    double acc[Cfg::MI][4][2];
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; i++)
+#pragma unroll
+      for (int jn = 0; jn < 4; jn++) { acc[i][jn][0] = 0.0; acc[i][jn][1] = 0.0; }
+
+    for (int kt = 0; kt < ktiles; kt++) {
+      if (threadIdx.x == 0) produce_one();
+      mbar_wait(bars + 8 * stage, phase);
+      const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES + a_row_off;
+      const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        double b_ev[4], b_od[4];
+#pragma unroll
+        for (int jn = 0; jn < 4; jn++) {
+          const uint32_t o = (uint32_t)((jn >> 1) * 2048 + h * 1024);
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b_ev[jn]) : "r"(sb + b_base[0][jn & 1] + o));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b_od[jn]) : "r"(sb + b_base[1][jn & 1] + o));
+        }
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; i++) {
+          double a_ev, a_od;
+          const uint32_t addr = sa + (uint32_t)i * 1024u + (h ? a_ch1 : a_ch0);
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a_ev), "=d"(a_od) : "r"(addr));
+#pragma unroll
+          for (int jn = 0; jn < 4; jn++) {
+            dmma(acc[i][jn][0], acc[i][jn][1], a_ev, b_ev[jn]);
+            dmma(acc[i][jn][0], acc[i][jn][1], a_od, b_od[jn]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (Cfg::STAGES + stage));
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // epilogue: C -= acc
+    const long long row_base = (long long)mt * GEMM_BM + warp_m * Cfg::WM + prow;
+    const long long col_base = (long long)nt * BN + warp_n * 32 + 2 * s4;
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; i++) {
+      const long long r = row_base + i * 8;
+      if (r >= P.m) continue;
+      double *crow = P.C + (P.rc + r) * P.ld + P.cc;
+      double2 cv[4];
+#pragma unroll
+      for (int jn = 0; jn < 4; jn++) {
+        const long long c = col_base + jn * 8;
+        if (c + 1 < P.n) cv[jn] = *reinterpret_cast<const double2 *>(crow + c);
+        else if (c < P.n) cv[jn] = make_double2(crow[c], 0.0);
+      }
+#pragma unroll
+      for (int jn = 0; jn < 4; jn++) {
+        const long long c = col_base + jn * 8;
+        if (c + 1 < P.n) {
+          *reinterpret_cast<double2 *>(crow + c) = make_double2(cv[jn].x - acc[i][jn][0], cv[jn].y - acc[i][jn][1]);
+        } else if (c < P.n) {
+          crow[c] = cv[jn].x - acc[i][jn][0];
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Host side: tensor maps and launch
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int lu_bind(UpdesLU *h, const double *K) {
+  if (h->bound == K) return 0;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  const cuuint64_t ld = (cuuint64_t)h->ld, n = (cuuint64_t)h->n;
+  {
+    // A operand: dims (columns, rows); box 16 columns x 128 rows
+    cuuint64_t dims[2] = {ld, n};
+    cuuint64_t strides[1] = {ld * 8};
+    cuuint32_t box[2] = {GEMM_BK, GEMM_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&h->mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)K, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  }
+  {
+    // B operand: box 16 columns x 16 k-rows; a BN-wide tile is BN/16 such boxes laid out
+    // [column group][k][16 columns], which keeps the k rows 128 B apart (conflict-free LDS.64)
+    cuuint64_t dims[2] = {ld, n};
+    cuuint64_t strides[1] = {ld * 8};
+    cuuint32_t box[2] = {16, GEMM_BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&h->mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)K, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  }
+  h->bound = K;
+  return 0;
+}
+
+template <int BN>
+static int launch_gemm(UpdesLU *h, const GemmParams &P, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(dgemm_sub_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long tiles = ((P.m + GEMM_BM - 1) / GEMM_BM) * ((P.n + BN - 1) / BN);
+  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  dgemm_sub_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(h->mapA, h->mapB, P);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+int dgemm_sub(UpdesLU *h, double *K, int64_t rc, int64_t cc, int64_t ra, int64_t ca, int64_t rb, int64_t cb,
+              int64_t m, int64_t n, int64_t k, cudaStream_t st) {
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  if (k % GEMM_BK) return -11;
+  if ((cc & 1) || (cb & 15) || (ca & 1)) return -4;
+  int rc_ = lu_bind(h, K);
+  if (rc_) return rc_;
+  GemmParams P;
+  P.C = K; P.ld = h->ld; P.rc = rc; P.cc = cc; P.ra = ra; P.ca = ca; P.rb = rb; P.cb = cb; P.m = m; P.n = n; P.k = k;
+  if (n <= 32) return launch_gemm<32>(h, P, st);
+  if (n <= 64) return launch_gemm<64>(h, P, st);
+  return launch_gemm<128>(h, P, st);
+}
+
+}  // namespace updes
+
+extern "C" int updes_dgemm_sub(UpdesLU *handle, double *K, int64_t rc, int64_t cc, int64_t ra, int64_t ca,
+                               int64_t rb, int64_t cb, int64_t m, int64_t n, int64_t k, void *stream) {
+  if (!handle) return -1;
+  if (!K) return -2;
+  return updes::dgemm_sub(handle, K, rc, cc, ra, ca, rb, cb, m, n, k, (cudaStream_t)stream);
+}

@@ -1,0 +1,129 @@
+// LU helpers on the row-major matrix: row interchanges, unit-lower triangular solve of a block
+// row (U12 = L11^-1 A12), pivot list -> permutation.
+#include "lu.cuh"
+
+namespace updes {
+
+// ---- row interchanges -------------------------------------------------------------------------
+// Applies interchanges (k0+t <-> ipiv[k0+t]), t = 0..npiv-1, in order, to columns [c0, c0+ncols).
+// Row-major storage makes every interchange a pair of fully coalesced row segments; one thread
+// owns two adjacent columns for the whole sequence, so the in-order semantics need no barrier.
+constexpr int SWAP_THREADS = 128;
+constexpr int SWAP_MAX_PIV = 64;
+
+__global__ void __launch_bounds__(SWAP_THREADS) swap_rows_kernel(double *K, long long ld, long long c0, long long ncols,
+                                                                long long k0, int npiv, const int32_t *ipiv) {
+  __shared__ int s_piv[SWAP_MAX_PIV];
+  if (threadIdx.x < npiv) s_piv[threadIdx.x] = ipiv[k0 + threadIdx.x];
+  __syncthreads();
+  const long long c = c0 + 2 * ((long long)blockIdx.x * SWAP_THREADS + threadIdx.x);
+  if (c >= c0 + ncols) return;
+  const bool pair = c + 1 < c0 + ncols;
+  for (int t = 0; t < npiv; t++) {
+    const long long p = s_piv[t];
+    if (p == k0 + t) continue;
+    double *ra = K + (k0 + t) * ld + c, *rb = K + p * ld + c;
+    if (pair) {
+      const double2 va = *reinterpret_cast<double2 *>(ra), vb = *reinterpret_cast<double2 *>(rb);
+      *reinterpret_cast<double2 *>(ra) = vb;
+      *reinterpret_cast<double2 *>(rb) = va;
+    } else {
+      const double va = *ra, vb = *rb;
+      *ra = vb; *rb = va;
+    }
+  }
+}
+
+int swap_rows(UpdesLU *h, double *K, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
+              cudaStream_t st) {
+  if (ncols <= 0 || npiv <= 0) return 0;
+  if (c0 & 1) return -3;
+  for (int64_t t0 = 0; t0 < npiv; t0 += SWAP_MAX_PIV) {
+    const int np = (int)((npiv - t0) < SWAP_MAX_PIV ? (npiv - t0) : SWAP_MAX_PIV);
+    const long long pairs = (ncols + 1) / 2;
+    swap_rows_kernel<<<(unsigned)((pairs + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
+        K, h->ld, c0, ncols, k0 + t0, np, ipiv);
+    UPDES_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- unit-lower triangular solve, base case ------------------------------------------------------
+// X = L^-1 B with L = K[r0:r0+NB, r0:r0+NB] (unit lower) and B = K[r0:r0+NB, c0:c0+ncols], in place.
+// One thread per column of B: the NB values of the column live in registers, L is broadcast from
+// shared memory; loads/stores are coalesced across the threads of a warp (adjacent columns).
+template <int NB>
+__global__ void __launch_bounds__(128) trsm_base_kernel(double *K, long long ld, long long r0, long long c0,
+                                                        long long ncols) {
+  __shared__ double L[NB][NB + 1];
+  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+    const int i = t / NB, j = t % NB;
+    L[i][j] = K[(r0 + i) * ld + r0 + j];
+  }
+  __syncthreads();
+  const long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c0 + ncols) return;
+  double x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++) x[i] = K[(r0 + i) * ld + c];
+#pragma unroll
+  for (int i = 1; i < NB; i++) {
+    double v = x[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) v = fma(-L[i][j], x[j], v);
+    x[i] = v;
+  }
+#pragma unroll
+  for (int i = 1; i < NB; i++) K[(r0 + i) * ld + c] = x[i];
+}
+
+static int trsm_base(UpdesLU *h, double *K, int64_t r0, int nb, int64_t c0, int64_t ncols, cudaStream_t st) {
+  const unsigned grid = (unsigned)((ncols + 127) / 128);
+  if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
+  else if (nb == 16) trsm_base_kernel<16><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
+  else if (nb == 8) trsm_base_kernel<8><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
+  else return -4;
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+// Recursive blocked solve: split L11, solve the top half, rank-update the bottom half with the
+// DMMA GEMM, solve the bottom half.  n1 is a multiple of the base width.
+int trsm_unit_lower(UpdesLU *h, double *K, int64_t r0, int64_t n1, int64_t c0, int64_t ncols, cudaStream_t st) {
+  if (n1 <= 0 || ncols <= 0) return 0;
+  if (n1 <= 32) return trsm_base(h, K, r0, (int)n1, c0, ncols, st);
+  int64_t hlf = (n1 / 2 + 31) / 32 * 32;
+  int rc = trsm_unit_lower(h, K, r0, hlf, c0, ncols, st);
+  if (rc) return rc;
+  rc = dgemm_sub(h, K, r0 + hlf, c0, r0 + hlf, r0, r0, c0, n1 - hlf, ncols, hlf, st);
+  if (rc) return rc;
+  return trsm_unit_lower(h, K, r0 + hlf, n1 - hlf, c0, ncols, st);
+}
+
+// ---- pivots -> permutation ------------------------------------------------------------------------
+// perm[i] = index of the original row that the interchanges leave at position i.
+__global__ void perm_init_kernel(int32_t *perm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm[i] = i;
+}
+__global__ void perm_apply_kernel(int32_t *perm, const int32_t *ipiv, int n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < n; k++) {
+    const int p = ipiv[k];
+    if (p != k) {
+      const int a = perm[k], b = perm[p];
+      perm[k] = b; perm[p] = a;
+    }
+  }
+}
+
+int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st) {
+  const int n = (int)h->n;
+  perm_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->perm, n);
+  UPDES_LAUNCH_CHECK();
+  perm_apply_kernel<<<1, 32, 0, st>>>(h->perm, ipiv, n);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace updes

@@ -1,0 +1,101 @@
+// Host driver of the dense LU with partial pivoting (P K = L U, in place, row-major).
+//
+// Replaces the reference's inverse + GEMM + QR chain (updes/assembly.py:87-90,:398-401,
+// updes/operators.py:612-616) by one factorisation of the collocation system.
+//
+// Recursive (Toledo-style) blocking: a block of nc columns is split in two; the left half is
+// factored recursively, the right half gets U12 = L11^-1 A12 (recursive triangular solve) and the
+// Schur update A22 -= L21 U12 (DMMA GEMM), then the right half is factored recursively.  All
+// O(n^3) work lands in the GEMM with the largest possible inner dimension.  Row interchanges are
+// applied to the rest of the matrix right after each base panel (32 pivots at a time), which keeps
+// every interchange kernel short and fully coalesced in the row-major layout.
+#include "lu.cuh"
+
+namespace updes {
+
+int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st);
+
+int lu_recursive(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, int32_t *info, cudaStream_t st) {
+  if (nc <= 0) return 0;
+  const int64_t n = h->n;
+  const int W = panel_width_for(h, n - r0);
+  if (W < 16) return -2;   // panel taller than the register-resident kernel supports
+  if (nc <= W) {
+    int rc = lu_panel_base(h, K, r0, (int)nc, ipiv, info, st);
+    if (rc) return rc;
+    rc = swap_rows(h, K, 0, r0, r0, nc, ipiv, st);
+    if (rc) return rc;
+    return swap_rows(h, K, r0 + nc, n - (r0 + nc), r0, nc, ipiv, st);
+  }
+  int64_t n1;
+  if (nc <= 32) n1 = 16;
+  else n1 = (nc / 2 + 31) / 32 * 32;
+  int rc = lu_recursive(h, K, r0, n1, ipiv, info, st);
+  if (rc) return rc;
+  const int64_t n2 = nc - n1;
+  rc = trsm_unit_lower(h, K, r0, n1, r0 + n1, n2, st);
+  if (rc) return rc;
+  rc = dgemm_sub(h, K, r0 + n1, r0 + n1, r0 + n1, r0, r0, r0 + n1, n - (r0 + n1), n2, n1, st);
+  if (rc) return rc;
+  return lu_recursive(h, K, r0 + n1, n2, ipiv, info, st);
+}
+
+}  // namespace updes
+
+extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
+  if (!handle) return -1;
+  if (n <= 0 || n > 0x7fffffff) return -2;
+  if (ld < n || (ld % 16)) return -3;
+  UpdesLU *h = new UpdesLU();
+  h->n = n; h->ld = ld;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t W = updes::PANEL_W;
+  if (e == cudaSuccess) e = cudaMalloc(&h->cand, sizeof(double) * 2 * h->num_sms * W);
+  if (e == cudaSuccess) e = cudaMalloc(&h->top, sizeof(double) * 2 * W);
+  if (e == cudaSuccess) e = cudaMalloc(&h->candval, sizeof(double) * 2 * h->num_sms);
+  if (e == cudaSuccess) e = cudaMalloc(&h->candrow, sizeof(int32_t) * 2 * h->num_sms);
+  if (e == cudaSuccess) e = cudaMalloc(&h->barrier, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->barrier, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * n * 4);
+  if (e != cudaSuccess) {
+    updes_lu_destroy(h);
+    return (int)e;
+  }
+  *handle = h;
+  return 0;
+}
+
+extern "C" int updes_lu_destroy(UpdesLU *h) {
+  if (!h) return 0;
+  cudaFree(h->cand); cudaFree(h->top); cudaFree(h->candval); cudaFree(h->candrow);
+  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf);
+  delete h;
+  return 0;
+}
+
+extern "C" int updes_lu_factor(UpdesLU *h, double *K, int32_t *ipiv, int32_t *info, void *stream) {
+  if (!h) return -1;
+  if (!K || (((uintptr_t)K) & 1023)) return -2;
+  if (!ipiv) return -3;
+  if (!info) return -4;
+  cudaStream_t st = (cudaStream_t)stream;
+  UPDES_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+  int rc = updes::lu_bind(h, K);
+  if (rc) return rc;
+  rc = updes::lu_recursive(h, K, 0, h->n, ipiv, info, st);
+  if (rc) return rc;
+  return updes::build_permutation(h, ipiv, st);
+}
+
+extern "C" int updes_lu_panel(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, int32_t *info,
+                              void *stream) {
+  if (!h) return -1;
+  if (!K) return -2;
+  return updes::lu_panel_base(h, K, r0, (int)nc, ipiv, info, (cudaStream_t)stream);
+}
+
+extern "C" const char *updes_b200_version(void) { return "updes_b200 0.1 (sm_100a)"; }
+extern "C" int64_t updes_launch_count(void) { return updes::g_launch_count; }

@@ -1,0 +1,265 @@
+// Base panel of the blocked LU: partial-pivoting factorisation of a tall block of JB columns.
+//
+// The whole panel lives in REGISTERS for the duration of the kernel: each thread owns RPT rows of
+// JB doubles (JB*RPT = 32), so a 90k x 32 panel is spread over 148 CTAs x 640 threads and global
+// memory is touched exactly twice (load, store).  Per column j:
+//   1. every CTA finds its local arg-max |a(i,j)| with warp shuffles (ties -> smallest row, as
+//      LAPACK's idamax) and PUBLISHES the candidate's whole row (JB doubles) next to (|v|, row);
+//      CTA 0 also publishes the row currently sitting at the diagonal position;
+//   2. ONE grid barrier (monotonic atomic counter, acquire/release);
+//   3. every CTA reduces the <=148 candidates, reads the winner's row, performs the row
+//      interchange on the registers it owns and applies the rank-1 update to its rows.
+// Publishing the candidate rows before the barrier is what keeps it at one barrier per column:
+// nobody has to ask the pivot owner for its row afterwards.
+// Launched cooperatively (all CTAs co-resident), grid <= number of SMs.
+#include "lu.cuh"
+#include <cooperative_groups.h>
+
+namespace updes {
+
+constexpr int PANEL_THREADS = 640;
+
+struct PanelParams {
+  double *K;
+  long long ld, n, r0;
+  int jb;              // columns in this panel (<= JB)
+  int rows_per_cta;    // R
+  int32_t *ipiv, *info;
+  double *cand, *top, *candval;
+  int32_t *candrow;
+  unsigned int *barrier;
+  unsigned int barrier_base;   // counter value when this launch starts
+  int num_ctas;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// (value, row) arg-max with LAPACK tie-breaking (first = smallest row index)
+__device__ __forceinline__ void argmax_combine(double &v, int &r, double ov, int orow) {
+  if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+}
+
+template <int JB, int RPT>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams P) {
+  __shared__ double s_wv[32];
+  __shared__ int s_wr[32];
+  __shared__ double s_prow[JB], s_trow[JB];
+  __shared__ int s_piv;
+
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int b = blockIdx.x;
+  const int jb = P.jb;
+  const long long cta_row0 = P.r0 + (long long)b * P.rows_per_cta;
+
+  // ---- load my rows ------------------------------------------------------------------
+  double a[RPT][JB];
+  long long myrow[RPT];
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    const int li = tid + q * T;
+    const long long row = cta_row0 + li;
+    const bool valid = li < P.rows_per_cta && row < P.n;
+    myrow[q] = valid ? row : -1;
+    if (valid) {
+      const double *src = P.K + row * P.ld + P.r0;
+      if (jb == JB) {
+#pragma unroll
+        for (int c = 0; c < JB; c += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(src + c);
+          a[q][c] = v.x; a[q][c + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < JB; c++) a[q][c] = c < jb ? src[c] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++) a[q][c] = 0.0;
+    }
+  }
+
+  unsigned int target = P.barrier_base;
+
+#pragma unroll
+  for (int j = 0; j < JB; j++) {
+    if (j < jb) {   // uniform
+      const long long diag = P.r0 + j;
+      const int par = j & 1;
+      // ---- 1. local candidate -----------------------------------------------------------
+      double bv = -1.0;
+      int br = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < RPT; q++)
+        if (myrow[q] >= diag) argmax_combine(bv, br, fabs(a[q][j]), (int)myrow[q]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, br, off);
+        argmax_combine(bv, br, ov, orow);
+      }
+      if (lane == 0) { s_wv[warp] = bv; s_wr[warp] = br; }
+      __syncthreads();
+      double cv = lane < nwarps ? s_wv[lane] : -1.0;
+      int cr = lane < nwarps ? s_wr[lane] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, cv, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, cr, off);
+        argmax_combine(cv, cr, ov, orow);
+      }
+      // ---- publish -------------------------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (myrow[q] >= 0 && myrow[q] == (long long)cr) {
+          double *dst = P.cand + ((size_t)par * P.num_ctas + b) * JB;
+#pragma unroll
+          for (int c = 0; c < JB; c++) dst[c] = a[q][c];
+        }
+        if (myrow[q] == diag) {
+          double *dst = P.top + (size_t)par * JB;
+#pragma unroll
+          for (int c = 0; c < JB; c++) dst[c] = a[q][c];
+        }
+      }
+      if (tid == 0) {
+        P.candval[par * P.num_ctas + b] = cv;
+        P.candrow[par * P.num_ctas + b] = cr;
+      }
+      __threadfence();
+      __syncthreads();
+      // ---- 2. grid barrier -------------------------------------------------------------------
+      target += (unsigned int)P.num_ctas;
+      if (tid == 0) {
+        atomicAdd(P.barrier, 1u);
+        // bounded spin: a lost arrival must not hang the device (info = -1 flags the failure)
+        unsigned int polls = 0;
+        while ((int)(ld_acquire_u32(P.barrier) - target) < 0) {
+          if (++polls > (1u << 24)) { atomicExch(P.info, -1); break; }
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      // ---- 3. winner -----------------------------------------------------------------------------
+      if (warp == 0) {
+        double wv = -1.0;
+        int wr = 0x7fffffff, wb = 0;
+        for (int c = lane; c < P.num_ctas; c += 32) {
+          const double ov = __ldcg(P.candval + par * P.num_ctas + c);
+          const int orow = __ldcg(P.candrow + par * P.num_ctas + c);
+          if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wb = c; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, wv, off);
+          const int orow = __shfl_xor_sync(0xffffffffu, wr, off);
+          const int ob = __shfl_xor_sync(0xffffffffu, wb, off);
+          if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wb = ob; }
+        }
+        const bool none = (wr == 0x7fffffff);   // no comparable candidate (NaN column): keep the diagonal row
+        if (none) { wr = (int)diag; wv = 0.0; }
+        if (lane < JB) {
+          const double t = __ldcg(P.top + (size_t)par * JB + lane);
+          s_trow[lane] = t;
+          s_prow[lane] = none ? t : __ldcg(P.cand + ((size_t)par * P.num_ctas + wb) * JB + lane);
+        }
+        if (lane == 0) {
+          s_piv = wr;
+          if (b == 0) {
+            P.ipiv[diag] = wr;
+            if (wv == 0.0) atomicCAS(P.info, 0, (int)diag + 1);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- 4. interchange + rank-1 update ------------------------------------------------------------
+      const long long piv = s_piv;
+      const double pval = s_prow[j];
+      const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (myrow[q] < diag) continue;
+        if (myrow[q] == diag) {
+#pragma unroll
+          for (int c = 0; c < JB; c++) a[q][c] = s_prow[c];
+          continue;
+        }
+        if (myrow[q] == piv) {
+#pragma unroll
+          for (int c = 0; c < JB; c++) a[q][c] = s_trow[c];
+        }
+        if (pval != 0.0) {
+          const double l = a[q][j] * rinv;
+          a[q][j] = l;
+#pragma unroll
+          for (int c = j + 1; c < JB; c++) a[q][c] = fma(-l, s_prow[c], a[q][c]);
+        }
+      }
+    }
+  }
+
+  // ---- store ---------------------------------------------------------------------------
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    if (myrow[q] < 0) continue;
+    double *dst = P.K + myrow[q] * P.ld + P.r0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(a[q][c], a[q][c + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++)
+        if (c < jb) dst[c] = a[q][c];
+    }
+  }
+}
+
+template <int JB, int RPT>
+static int launch_panel(UpdesLU *h, PanelParams &P, int threads, cudaStream_t st) {
+  void *args[] = {&P};
+  UPDES_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<JB, RPT>, dim3(P.num_ctas), dim3(threads), args,
+                                             0, st));
+  ++g_launch_count;
+  return 0;
+}
+
+// widest base panel the register-resident kernel can take for a panel of m rows
+int panel_width_for(const UpdesLU *h, int64_t m) {
+  const int64_t cap = (int64_t)h->num_sms * PANEL_THREADS;
+  if (m <= cap) return 32;
+  if (m <= 2 * cap) return 16;
+  if (m <= 4 * cap) return 8;
+  return 0;
+}
+
+int lu_panel_base(UpdesLU *h, double *K, int64_t r0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st) {
+  const int64_t m = h->n - r0;
+  if (m <= 0 || jb <= 0) return 0;
+  const int JBmax = panel_width_for(h, m);
+  if (JBmax == 0) return -3;
+  if (jb > JBmax) return -4;
+  const int rpt = 32 / JBmax;
+  // rows per CTA: enough CTAs to fill the machine, at least 64 rows each, a multiple of 32
+  int ctas = (int)((m + 63) / 64);
+  if (ctas > h->num_sms) ctas = h->num_sms;
+  int64_t R = (m + ctas - 1) / ctas;
+  R = (R + 31) / 32 * 32;
+  ctas = (int)((m + R - 1) / R);
+  int threads = (int)((R + rpt - 1) / rpt);
+  threads = (threads + 31) / 32 * 32;
+  if (threads > PANEL_THREADS) return -3;
+  if (R < jb && ctas > 1) return -3;
+  PanelParams P;
+  P.K = K; P.ld = h->ld; P.n = h->n; P.r0 = r0; P.jb = jb; P.rows_per_cta = (int)R;
+  P.ipiv = ipiv; P.info = info; P.cand = h->cand; P.top = h->top; P.candval = h->candval; P.candrow = h->candrow;
+  P.barrier = h->barrier; P.barrier_base = h->barrier_count; P.num_ctas = ctas;
+  h->barrier_count += (unsigned int)ctas * (unsigned int)jb;
+  if (JBmax == 32) return launch_panel<32, 1>(h, P, threads, st);
+  if (JBmax == 16) return launch_panel<16, 2>(h, P, threads, st);
+  return launch_panel<8, 4>(h, P, threads, st);
+}
+
+}  // namespace updes

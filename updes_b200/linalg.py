@@ -1,0 +1,74 @@
+"""Dense FP64 LU with partial pivoting on the GPU: factor once, solve many.
+
+Replaces the reference's ``jnp.linalg.inv`` (assembly.py:87-90) + ``diffMat @ inv_A`` (:399) +
+``lineax.QR`` solve (operators.py:612-613) + second ``inv(A)`` matvec (:616) by one in-place
+factorisation ``P K = L U`` of the collocation system and two triangular sweeps per right-hand side.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _lib
+
+
+class LUFactorization:
+    """Owns the factors (in place in ``K``), the pivots and the native handle."""
+
+    def __init__(self, K, n=None):
+        torch = _lib.require_cuda()
+        self._lib = _lib.load()
+        assert K.dtype == torch.float64 and K.is_cuda and K.dim() == 2 and K.is_contiguous()
+        self.n = K.shape[0] if n is None else n
+        self.ld = K.shape[1]
+        self.K = K
+        self.ipiv = torch.empty(self.n, dtype=torch.int32, device=K.device)
+        self.info = torch.zeros(1, dtype=torch.int32, device=K.device)
+        handle = ctypes.c_void_p()
+        _lib.check(self._lib.updes_lu_create(ctypes.byref(handle), self.n, self.ld), "updes_lu_create")
+        self._handle = handle
+        self.factored = False
+
+    def factor(self):
+        """Enqueue the factorisation on the current stream (asynchronous)."""
+        rc = self._lib.updes_lu_factor(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(), self.info.data_ptr(),
+                                       _lib.stream_ptr())
+        _lib.check(rc, "updes_lu_factor")
+        self.factored = True
+        return self
+
+    def zero_pivot(self) -> int:
+        """0, or the 1-based index of the first exactly-zero pivot (synchronises)."""
+        return int(self.info.item())
+
+    def solve(self, B):
+        """Solve K X = B in place.  B: (nrhs, ldb>=n) or (n,) CUDA float64; returns B."""
+        assert self.factored
+        single = B.dim() == 1
+        Bm = B.view(1, -1) if single else B
+        assert Bm.is_contiguous() and Bm.shape[1] >= self.n
+        rc = self._lib.updes_lu_solve(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(), Bm.data_ptr(),
+                                      Bm.shape[1], Bm.shape[0], 0, _lib.stream_ptr())
+        _lib.check(rc, "updes_lu_solve")
+        return B
+
+    def gemm_sub(self, rc_, cc, ra, ca, rb, cb, m, n, k):
+        """C -= A @ B on sub-blocks of the bound matrix (exposed for kernel-level tests)."""
+        rc = self._lib.updes_dgemm_sub(self._handle, self.K.data_ptr(), rc_, cc, ra, ca, rb, cb, m, n, k,
+                                       _lib.stream_ptr())
+        _lib.check(rc, "updes_dgemm_sub")
+
+    def panel(self, r0, nc):
+        rc = self._lib.updes_lu_panel(self._handle, self.K.data_ptr(), r0, nc, self.ipiv.data_ptr(),
+                                      self.info.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "updes_lu_panel")
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.updes_lu_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
