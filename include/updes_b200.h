@@ -21,7 +21,7 @@
  *     (cudaError_t) raised while enqueuing.  Numerical status (LAPACK-style "zero pivot at
  *     column k", 1-based) is written to a device int32 `info` so no call forces a sync;
  *   - matrices are ROW-MAJOR with leading dimension `ld` (elements); `ld` must be a multiple
- *     of 16 (128-byte rows: TMA tiles, 16-byte vector stores) and the base 1024-byte aligned;
+ *     of 16 (128-byte rows: TMA tiles, 16-byte vector stores) and the base 128-byte aligned;
  *   - all arithmetic is FP64 (reference default, updes/config.py:15-16).
  */
 #ifndef UPDES_B200_H
@@ -125,6 +125,12 @@ int updes_lu_panel(UpdesLU *handle, double *K, int64_t r0, int64_t nc, int32_t *
 const char *updes_b200_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t updes_launch_count(void);
+/* Optional CUDA-event timing per kernel class (bench.py's roofline legs).  enable(1) clears the
+ * records and starts recording on the launching stream; read() synchronises and returns the summed
+ * milliseconds, work (flops for 0-3, bytes for 4-5) and launch count of one class:
+ * 0 trailing-update GEMM, 1 panel, 2 row interchanges, 3 triangular base solve, 4 assembly, 5 solve. */
+int updes_profile_enable(int on);
+int updes_profile_read(int cat, double *ms, double *work, int64_t *count);
 
 #ifdef __cplusplus
 }

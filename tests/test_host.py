@@ -1,0 +1,198 @@
+"""Host logic and ABI surface (CPU only): clouds vs the oracle's literal restatement, operator
+lowering, BC preparation, row descriptors, and that the C-ABI library loads and exports every
+symbol declared in include/updes_b200.h (no compute calls without a GPU)."""
+import os
+import re
+from functools import partial
+
+import numpy as np
+import pytest
+
+import updes_b200 as u
+from updes_b200 import assembly as asm
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, laplace_op
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_MESH = "/root/reference/updes/tests/data/mesh.msh"
+
+
+def _same_cloud(a, b):
+    assert (a.N, a.Ni, a.Nd, a.Nn, a.Nr, list(a.Np)) == (b.N, b.Ni, b.Nd, b.Nn, b.Nr, list(b.Np))
+    assert np.array_equal(a.sorted_nodes, b.sorted_nodes)
+    assert np.array_equal(a.sorted_outward_normals, b.sorted_outward_normals)
+    assert a.facet_nodes == b.facet_nodes and a.facet_types == b.facet_types
+    assert a.node_types == b.node_types and a.renumbering_map == b.renumbering_map
+
+
+@pytest.mark.parametrize("facets", [CONFIG1_FACETS, CONFIG2_FACETS,
+                                    {"South": "r", "West": "n", "North": "d", "East": "p1"},
+                                    {"North": "p3", "East": "r", "West": "r", "South": "p3"},
+                                    {k: "d" for k in ("South", "West", "North", "East")}])
+@pytest.mark.parametrize("shape,seed", [((9, 7), None), ((6, 11), 3), ((30, 20), None)])
+def test_square_cloud_matches_reference_restatement(oracle, facets, shape, seed):
+    a = u.SquareCloud(Nx=shape[0], Ny=shape[1], facet_types=facets, noise_key=seed)
+    b = oracle.RefSquareCloud(shape[0], shape[1], facets, noise_seed=seed)
+    _same_cloud(a, b)
+
+
+def test_square_cloud_counts_of_the_configs():
+    c1 = u.SquareCloud(Nx=30, Ny=20, facet_types=CONFIG1_FACETS)
+    assert (c1.N, c1.Ni, c1.Nd, c1.Nn) == (600, 504, 66, 30)
+    c2 = u.SquareCloud(Nx=35, Ny=35, facet_types=CONFIG2_FACETS)
+    assert (c2.N, c2.Ni, c2.Np) == (1225, 1089, [70, 66])
+    # periodic pairs (i, i + Np/2) are geometric opposites
+    s = c2.Ni
+    for g, nb in enumerate(c2.Np):
+        xy1, xy2 = c2.sorted_nodes[s:s + nb // 2], c2.sorted_nodes[s + nb // 2:s + nb]
+        same = 0 if g == 0 else 1
+        assert np.allclose(xy1[:, same], xy2[:, same])
+        s += nb
+    c4 = u.SquareCloud(Nx=300, Ny=300, facet_types=CONFIG1_FACETS)
+    assert (c4.N, c4.Ni) == (90000, 88804)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MESH), reason="reference fixture not mounted (GPU box)")
+@pytest.mark.parametrize("tag,facets", [("vel", {"Wall": "d", "Inflow": "d", "Outflow": "n", "Blowing": "d", "Suction": "d"}),
+                                        ("phi", {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"})])
+def test_gmsh_cloud_on_reference_fixture(oracle, tag, facets):
+    """updes/tests/data/mesh.msh: product reader == literal restatement == committed golden arrays."""
+    a = u.GmshCloud(REF_MESH, facet_types=facets)
+    _same_cloud(a, oracle.RefGmshCloud(REF_MESH, facets))
+    g = np.load(os.path.join(GOLDEN, "mesh_msh_cloud_%s.npz" % tag))
+    assert np.array_equal(a.sorted_nodes, g["sorted_nodes"])
+    assert np.array_equal(a.sorted_outward_normals, g["sorted_outward_normals"])
+    assert list(g["counts"]) == [a.N, a.Ni, a.Nd, a.Nn, a.Nr]
+    assert a.N == 1385 and a.Ni == 1227
+    assert np.allclose(np.linalg.norm(a.sorted_outward_normals, axis=1), 1.0)
+
+
+def test_gmsh_reader_on_generated_mesh(tmp_path, oracle):
+    """A Gmsh-4.0 ASCII channel mesh written by tests/golden/make_msh.py (own data)."""
+    from golden.make_msh import write_channel_msh
+    path = str(tmp_path / "channel.msh")
+    write_channel_msh(path, nx=13, ny=9)
+    facets = {"Wall": "d", "Inflow": "n", "Outflow": "r"}
+    a = u.GmshCloud(path, facet_types=facets)
+    _same_cloud(a, oracle.RefGmshCloud(path, facets))
+    assert a.N == 13 * 9 and a.Ni == 11 * 7
+    # inflow normals point to -x, outflow to +x
+    inflow = [i - a.Ni - a.Nd for i in a.facet_nodes["Inflow"]]
+    assert np.allclose(a.sorted_outward_normals[inflow], [-1.0, 0.0])
+
+
+def test_rbf_identification():
+    assert u.identify_rbf(u.polyharmonic) == ("polyharmonic", 1.0)
+    assert u.identify_rbf(partial(u.polyharmonic, a=2)) == ("polyharmonic", 2.0)
+    assert u.identify_rbf(partial(u.gaussian, eps=10.0)) == ("gaussian", 10.0)
+    assert u.identify_rbf(partial(partial(u.thin_plate, a=3))) == ("thin_plate", 3.0)
+    with pytest.raises(TypeError):
+        u.identify_rbf(lambda x, c: 0.0)
+    with pytest.raises(TypeError):
+        u.identify_rbf(partial(u.gaussian, a=1))
+    assert u.compute_nb_monomials(1, 2) == 3 and u.compute_nb_monomials(4, 2) == 15
+    with pytest.raises(NotImplementedError):
+        u.compute_nb_monomials(5, 2)
+
+
+def test_operator_lowering_of_the_shipped_operators():
+    cloud = u.SquareCloud(Nx=9, Ny=7, facet_types=CONFIG1_FACETS)
+    Ni = cloud.Ni
+    lap, _ = u.lower_diff_operator(laplace_op(u), cloud, u.polyharmonic)
+    assert np.array_equal(lap, np.tile([0, 0, 0, 1.0, 1.0], (Ni, 1)))                     # README.md:46-47
+    adv, adv_p = u.lower_diff_operator(advdiff_op(u), cloud, u.polyharmonic)
+    assert np.allclose(adv, np.tile([1e4, 100.0, 0.0, -0.08, -0.08], (Ni, 1))) and np.array_equal(adv, adv_p)
+    # Navier-Stokes momentum: U . grad - lap / Re with fields = (u, v)   (demos/NavierStokes/30_...:61-65)
+    uu, vv = np.linspace(0, 1, cloud.N), np.linspace(2, 3, cloud.N)
+
+    def ns(x, center, rbf, monomial, fields):
+        U = np.array([fields[0], fields[1]])
+        return u.dot(U, u.nodal_gradient(x, center, rbf, monomial)) - u.nodal_laplacian(x, center, rbf, monomial) / 100.0
+    c, _ = u.lower_diff_operator(ns, cloud, u.polyharmonic, [uu, vv])
+    assert np.allclose(c[:, 1], uu[:Ni]) and np.allclose(c[:, 2], vv[:Ni]) and np.allclose(c[:, 3:], -0.01)
+    # Darcy: -div(k grad) through nodal_div_grad with a per-row field   (demos/Darcy/00_darcy_flow.py:85-89)
+    kk = np.linspace(1, 2, cloud.N)
+    darcy = lambda x, center, rbf, monomial, fields: -u.nodal_div_grad(x, center, rbf, monomial, (fields[0], fields[0]))
+    c, _ = u.lower_diff_operator(darcy, cloud, u.gaussian, [kk])
+    assert np.allclose(c[:, 3], -kk[:Ni]) and np.allclose(c[:, 4], -kk[:Ni]) and np.all(c[:, :3] == 0)
+    # coefficients may depend on x
+    c, _ = u.lower_diff_operator(lambda x, ce, r, m, f: np.sin(x[0]) * u.nodal_value(x, ce, r, m), cloud, u.gaussian)
+    assert np.allclose(c[:, 0], np.sin(cloud.sorted_nodes[:Ni, 0]))
+
+
+@pytest.mark.parametrize("bad", [
+    lambda x, c, r, m, f: u.nodal_value(x, c, r, m) * u.nodal_gradient(x, c, r, m)[0],       # demos/NavierStokes/10_...:89-94
+    lambda x, c, r, m, f: u.nodal_value(x, c, r, m) ** 2,
+    lambda x, c, r, m, f: 1.0 / u.nodal_laplacian(x, c, r, m),
+    lambda x, c, r, m, f: u.nodal_value(x, c, r, m) + 1.0,
+    lambda x, c, r, m, f: 3.0,
+    lambda x, c, r, m, f: np.exp(u.nodal_value(x, c, r, m)),
+    lambda x, c, r, m, f: r(x, c),
+])
+def test_operators_outside_the_term_set_raise(bad):
+    cloud = u.SquareCloud(Nx=6, Ny=5, facet_types=CONFIG1_FACETS)
+    with pytest.raises((u.OperatorLoweringError, TypeError)):
+        u.lower_diff_operator(bad, cloud, u.polyharmonic)
+
+
+def test_bc_preparation_matches_reference_rules():
+    cloud = u.SquareCloud(Nx=8, Ny=6, facet_types={"South": "r", "West": "d", "North": "p1", "East": "n"})
+    bcs = {"South": (lambda c: c[0], lambda c: 2.0 + c[0]), "West": lambda c: 1.0, "North": lambda c: 5.0, "East": 0.5}
+    arr = u.boundary_conditions_func_to_arr(bcs, cloud)
+    south = np.asarray(cloud.facet_nodes["South"])
+    assert np.allclose(arr["South"][0], cloud.sorted_nodes[south, 0]) and np.allclose(arr["South"][1], 2 + cloud.sorted_nodes[south, 0])
+    robin, new = u.duplicate_robin_coeffs(arr, cloud)
+    assert sorted(robin) == sorted(south.tolist()) and np.allclose([robin[i] for i in south], 2 + cloud.sorted_nodes[south, 0])
+    assert np.allclose(new["South"], cloud.sorted_nodes[south, 0])
+    new = u.zerofy_periodic_cond(new, cloud)
+    assert np.all(new["North"] == 0)
+    with pytest.raises(ValueError):                                               # reference: AttributeError (Q6)
+        u.duplicate_robin_coeffs({**arr, "South": np.zeros(len(south))}, cloud)
+
+
+def test_row_descriptors_periodic_layout():
+    """Boundary row order d, n, r, periodic-value rows of all groups, then periodic-flux rows (assembly.py:157-267)."""
+    cloud = u.SquareCloud(Nx=7, Ny=7, facet_types=CONFIG2_FACETS)
+    t = asm.build_operator_rows(cloud, np.tile([0, 0, 0, 1.0, 1.0], (cloud.Ni, 1)))
+    Ni, (n0, n1) = cloud.Ni, cloud.Np
+    half = (n0 + n1) // 2
+    v0 = np.arange(Ni, Ni + n0 // 2)
+    assert np.array_equal(t.p1[v0], v0) and np.array_equal(t.p2[v0], v0 + n0 // 2) and np.all(t.skip[v0] == -1)
+    v1 = np.arange(Ni + n0 // 2, Ni + half)
+    assert np.array_equal(t.p1[v1], np.arange(Ni + n0, Ni + n0 + n1 // 2))
+    f0 = v0 + half
+    assert np.array_equal(t.p1[f0], v0) and np.all(t.cphi1[f0, 0] == 0) and np.all(t.cphi1[v0, 0] == 1) and np.all(t.cphi2[v0, 0] == -1)
+    assert np.array_equal(t.skip[:Ni], np.arange(Ni))
+    assert t.masks() == (asm.JET_HESS | asm.JET_GRAD, asm.JET_VAL | asm.JET_GRAD)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from updes_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "updes_b200.h")).read()
+    declared = set(re.findall(r"\b(updes_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "libupdes_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
+    assert b"sm_100a" in lib.updes_b200_version()
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cloud = u.SquareCloud(Nx=6, Ny=5, facet_types=CONFIG1_FACETS)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        u.pde_solver(laplace_op(u), lambda x, c, r, f: 0.0, cloud, {k: (lambda c: 0.0) for k in cloud.facet_types},
+                     u.polyharmonic, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        u.value(np.zeros(2), np.zeros(33), cloud.sorted_nodes, u.polyharmonic)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "updes_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f

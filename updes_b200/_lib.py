@@ -37,6 +37,8 @@ SIGNATURES = {
     "updes_lu_panel": (_I32, [_VP, _VP, _I64, _I64, _VP, _VP, _VP]),
     "updes_b200_version": (ctypes.c_char_p, []),
     "updes_launch_count": (_I64, []),
+    "updes_profile_enable": (_I32, [_I32]),
+    "updes_profile_read": (_I32, [_I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 }
 
 _lib = None
@@ -81,3 +83,18 @@ def stream_ptr():
 
 def launch_count() -> int:
     return int(load().updes_launch_count())
+
+
+PROF_CLASSES = {"gemm": 0, "panel": 1, "swap": 2, "trsm": 3, "assemble": 4, "solve": 5}
+
+
+def profile_enable(on: bool):
+    load().updes_profile_enable(1 if on else 0)
+
+
+def profile_read(name: str):
+    """(milliseconds, work, launches) of one kernel class since profile_enable(True)."""
+    ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    check(load().updes_profile_read(PROF_CLASSES[name], ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt)),
+          "updes_profile_read")
+    return ms.value, work.value, cnt.value

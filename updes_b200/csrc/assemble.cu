@@ -184,7 +184,9 @@ static int assemble_block_impl(int kind, double param, int N, int M, const doubl
       P.col0 = col0; P.ncols = cphi_end - col0; P.out = out; P.ld = ld;
       P.ip = (int)param; P.e2 = param * param;
       int rc = 0;
+      prof_begin(PROF_ASSEMBLE, 8.0 * (double)P.nrows * (double)P.ncols, st);
       UPDES_DISPATCH_KIND(kind, rc = launch_phi<KIND>(jet_mask, P, st));
+      prof_end(st);
       if (rc) return rc;
     }
     if (col0 + ncols > N) {

@@ -17,6 +17,11 @@ namespace updes {
 
 extern long long g_launch_count;   // kernels launched by this library (bench.py gpu_launches)
 
+// optional event timing per kernel class (profile.cu); work = flops or bytes of the launch
+enum { PROF_GEMM = 0, PROF_PANEL = 1, PROF_SWAP = 2, PROF_TRSM = 3, PROF_ASSEMBLE = 4, PROF_SOLVE = 5, PROF_JETS = 6 };
+void prof_begin(int cat, double work, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
 #define UPDES_CUDA_TRY(expr)                       \
   do {                                             \
     cudaError_t _e = (expr);                       \

@@ -301,7 +301,9 @@ static int launch_gemm(UpdesLU *h, const GemmParams &P, cudaStream_t st) {
   }
   const long long tiles = ((P.m + GEMM_BM - 1) / GEMM_BM) * ((P.n + BN - 1) / BN);
   const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
   dgemm_sub_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(h->mapA, h->mapB, P);
+  prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
 }

@@ -41,8 +41,10 @@ int swap_rows(UpdesLU *h, double *K, int64_t c0, int64_t ncols, int64_t k0, int6
   for (int64_t t0 = 0; t0 < npiv; t0 += SWAP_MAX_PIV) {
     const int np = (int)((npiv - t0) < SWAP_MAX_PIV ? (npiv - t0) : SWAP_MAX_PIV);
     const long long pairs = (ncols + 1) / 2;
+    prof_begin(PROF_SWAP, 32.0 * (double)ncols * np, st);
     swap_rows_kernel<<<(unsigned)((pairs + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
         K, h->ld, c0, ncols, k0 + t0, np, ipiv);
+    prof_end(st);
     UPDES_LAUNCH_CHECK();
   }
   return 0;
@@ -79,10 +81,12 @@ __global__ void __launch_bounds__(128) trsm_base_kernel(double *K, long long ld,
 
 static int trsm_base(UpdesLU *h, double *K, int64_t r0, int nb, int64_t c0, int64_t ncols, cudaStream_t st) {
   const unsigned grid = (unsigned)((ncols + 127) / 128);
+  prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
   if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
   else if (nb == 16) trsm_base_kernel<16><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
   else if (nb == 8) trsm_base_kernel<8><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
   else return -4;
+  prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
 }

@@ -78,7 +78,7 @@ extern "C" int updes_lu_destroy(UpdesLU *h) {
 
 extern "C" int updes_lu_factor(UpdesLU *h, double *K, int32_t *ipiv, int32_t *info, void *stream) {
   if (!h) return -1;
-  if (!K || (((uintptr_t)K) & 1023)) return -2;
+  if (!K || (((uintptr_t)K) & 127)) return -2;   // rows must be whole 128-byte lines
   if (!ipiv) return -3;
   if (!info) return -4;
   cudaStream_t st = (cudaStream_t)stream;

@@ -220,8 +220,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
 template <int JB, int RPT>
 static int launch_panel(UpdesLU *h, PanelParams &P, int threads, cudaStream_t st) {
   void *args[] = {&P};
-  UPDES_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<JB, RPT>, dim3(P.num_ctas), dim3(threads), args,
-                                             0, st));
+  prof_begin(PROF_PANEL, (double)(P.n - P.r0) * P.jb * P.jb, st);
+  cudaError_t le = cudaLaunchCooperativeKernel((void *)lu_panel_kernel<JB, RPT>, dim3(P.num_ctas), dim3(threads), args,
+                                               0, st);
+  prof_end(st);
+  if (le != cudaSuccess) return (int)le;
   ++g_launch_count;
   return 0;
 }

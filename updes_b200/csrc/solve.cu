@@ -158,7 +158,9 @@ extern "C" int updes_lu_solve(UpdesLU *h, const double *LU, const int32_t *ipiv,
     double *Bf = B + (long long)f0 * ldb;
     gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf);
     UPDES_LAUNCH_CHECK();
+    prof_begin(PROF_SOLVE, 8.0 * (double)n * (double)n, st);
     int rc = solve_chunk(h, LU, h->xbuf, nf, st);
+    prof_end(st);
     if (rc) return rc;
     copy_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, n, h->xbuf);
     UPDES_LAUNCH_CHECK();
