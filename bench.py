@@ -18,8 +18,12 @@ the collocation system in HBM, in-place LU with partial pivoting, one right-hand
            quotes as "19 minutes"), expressed in the same unit as (2/3 n_s^3) / seconds.  JAX is not
            installed in this image, so this is the oracle port, not the reference package itself.
 
-Multi-GPU: until the block-cyclic LU lands, --gpus N runs N independent replicas of the same
-problem ("scaling": "weak", config.parallelism says so).
+Multi-GPU (--gpus N, one process per GPU under torchrun): ONE problem sharded column-block-cyclically
+over the N GPUs (updes_b200/distributed.py): assembly of the owned column blocks (no communication),
+LU with one NCCL broadcast per panel, distributed solve.  The problem grows with N so that every GPU
+keeps the 1-GPU HBM footprint (64.8 GB of matrix): side = 300 N^(1/4) -> 300, 357, 424, 500 nodes per
+side, i.e. BASELINE.json's 500x500 / 250k-node configuration at N = 8 ("scaling": "weak" in memory per
+GPU; flops per GPU grow as sqrt(N), so the metric is TFLOP/s, not seconds).
 """
 import argparse
 import json
@@ -99,7 +103,7 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args.nx), "sample": "SquareCloud %dx%d" % (nx, nx)},
+            "config": {"workload": workload_name(args.nx or int(round(300 * args.gpus ** 0.25))), "sample": "SquareCloud %dx%d" % (nx, nx)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -158,7 +162,9 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    nx = args.nx
+    nx = args.nx if args.nx else int(round(300 * world ** 0.25))
+    if world > 1:
+        return run_gpu_arm_distributed(args, world, rank, local, nx)
     cloud = u.SquareCloud(Nx=nx, Ny=nx, facet_types=FACETS)
     M = 3
     n = cloud.N + M
@@ -302,7 +308,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(nx), "n": n, "matrix_bytes": 8 * n * n, "lu_flops": lu_flops(n),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (block-cyclic LU not built yet)" % world,
+                       "parallelism": "1 GPU",
                        "l2": "matrix (%.1f GB) is far larger than L2; no flush needed" % (8 * n * n / 1e9)},
             "seconds_per_step": ms_step * 1e-3,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -316,13 +322,139 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_gpu_arm_distributed(args, world, rank, local, nx):
+    """N > 1: one sharded problem (column-block-cyclic), timed as the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import updes_b200 as u
+    from updes_b200 import _lib, assembly as asm
+    from updes_b200.distributed import ColumnBlockCyclic, CudaBackend, DistributedLU
+    from updes_b200.operators import default_block_width
+
+    cloud = u.SquareCloud(Nx=nx, Ny=nx, facet_types=FACETS)
+    M = 3
+    n = cloud.N + M
+    coef = np.tile([0.0, 0, 0, 1.0, 1.0], (cloud.Ni, 1))
+    table = asm.build_operator_rows(cloud, coef)
+    rows = asm.DeviceRows(cloud, table)
+    xy = cloud.sorted_nodes
+    q = np.zeros(n)
+    north = np.asarray(cloud.facet_nodes["North"])
+    q[north] = np.sin(np.pi * xy[north, 0])
+    nb = args.nb or default_block_width(n, world)
+    layout = ColumnBlockCyclic(n, nb, world)
+    be = CudaBackend(layout, rank, gemm_sms_reserved=args.reserve_sms)
+    dlu = DistributedLU(layout, rank, be)
+    b = be.vector(q)
+    state = {}
+
+    def step():
+        be.info.zero_()
+        be.assemble(rows, "polyharmonic", 1.0, M)
+        dlu.factor()
+        state["x"] = dlu.solve(b)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.profile_enable(True)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    prof = {k: _lib.profile_read(k) for k in ("gemm", "panel", "swap", "trsm", "assemble")}
+    _lib.profile_enable(False)
+    value = lu_flops(n) / (ms_step * 1e-3) * 1e-12
+
+    x = state["x"]
+    r = b - asm.apply_rows(rows, "polyharmonic", 1.0, M, x.view(1, -1))[0]
+    own = torch.arange(cloud.N, dtype=torch.int32, device="cuda")
+    jphi, jpol = asm.eval_jets("polyharmonic", 1.0, rows.centres, x.view(1, -1), rows.centres, own)
+    vals = (jphi[0, :, 0] + jpol[0, :, 0]).cpu().numpy()
+    exact = np.sin(np.pi * xy[:, 0]) * np.cosh(np.pi * xy[:, 1]) / np.cosh(np.pi)
+    max_err = float(np.max(np.abs(vals - exact)))
+    # ||K||_inf from the owned column blocks (row sums add across ranks)
+    be.assemble(rows, "polyharmonic", 1.0, M)
+    rs = be.local[:, :be.cols].abs().sum(dim=1)
+    dist.all_reduce(rs)
+    berr = float(r.abs().max().item() / (rs.max().item() * x.abs().max().item() + b.abs().max().item()))
+    zero_piv = be.info.clone(); dist.all_reduce(zero_piv, op=dist.ReduceOp.MAX)
+
+    # e2e: the public API with host inputs, sharded the same way (every rank calls pde_solver_jit)
+    del be, dlu
+    torch.cuda.empty_cache()
+    op = lambda xx, center, rbf, monomial, fields: u.nodal_laplacian(xx, center, rbf, monomial)
+    rhs = lambda xx, centers, rbf, fields: 0.0
+    bcs = {"South": np.zeros(len(cloud.facet_nodes["South"])), "West": np.zeros(len(cloud.facet_nodes["West"])),
+           "North": np.sin(np.pi * xy[north, 0]), "East": np.zeros(len(cloud.facet_nodes["East"]))}
+    e2e_s = 0.0
+    for i in range(args.e2e_steps + 1):
+        u.clear_cache(); torch.cuda.empty_cache(); barrier()
+        t0 = time.perf_counter()
+        sol = u.pde_solver_jit(op, rhs, cloud, bcs, u.polyharmonic, 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0 or args.e2e_steps == 0:
+            e2e_s = max(e2e_s, dt)
+    u.clear_cache()
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = int(world * (xy.nbytes + sum(getattr(table, k).nbytes for k in ("p1", "p2", "cphi1", "cphi2", "cpol1", "cpol2", "skip")) + 16 * n))
+    d2h = int(world * (8 * n + 8 * cloud.N + 4))
+    if rank == 0:
+        fp64_peak = 37.0
+        try:
+            fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r01_ceilings.json")))["dmma_tflops_8warps"])
+        except Exception:
+            pass
+        g_ms, g_flops, g_cnt = prof["gemm"]
+        gemm_tf = g_flops / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(nx), "n": n, "matrix_bytes": 8 * n * n, "lu_flops": lu_flops(n),
+                           "parallelism": "1x%d column-block-cyclic, nb=%d, look-ahead 1, NCCL panel broadcast" % (world, nb),
+                           "matrix_bytes_per_gpu": 8 * n * n // world,
+                           "l2": "local matrix (%.1f GB) is far larger than L2; no flush needed" % (8 * n * n / world / 1e9)},
+                "seconds_per_step": ms_step * 1e-3,
+                "e2e": {"value": lu_flops(n) / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "seconds_per_step": e2e_s, "api": "updes_b200.pde_solver_jit on every rank (numpy in, numpy out)",
+                        "max_err_vs_analytic": float(np.max(np.abs(sol.vals - exact)))},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "dgemm_sub_kernel<128> on rank 0", "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak,
+                             "unit": "TFLOP/s", "frac": gemm_tf / fp64_peak, "traffic": None,
+                             "share_of_step": g_ms / (ms_step * args.steps),
+                             "peak_source": "raw DMMA issue rate per GPU, profiles/r01_ceilings.json"},
+                "breakdown": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] // max(args.steps, 1)} for k, v in prof.items()},
+                "per_gpu_tflops": value / world, "cpu_baseline": None,
+                "correctness": {"backward_error": berr, "max_err_vs_analytic": max_err, "zero_pivot": int(zero_piv.item())}}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nx", type=int, default=300, help="SquareCloud side (300 -> the 90k-node headline config)")
+    ap.add_argument("--nx", type=int, default=0, help="SquareCloud side (default 300 * gpus^(1/4): 300 -> the 90k-node headline config)")
+    ap.add_argument("--nb", type=int, default=0, help="column-block width of the multi-GPU layout (default: auto)")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="SMs left free by the update GEMM for NCCL (multi-GPU)")
     ap.add_argument("--cpu-nx", type=int, default=70, help="side of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")

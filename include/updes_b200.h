@@ -77,6 +77,9 @@ typedef struct UpdesRows {
 #define UPDES_JET_VAL 1
 #define UPDES_JET_GRAD 2
 #define UPDES_JET_HESS 4
+/* every row in the range is c0*phi + c3*(phi_xx + phi_yy) (no gradient term, c3 == c4): the kernel
+ * then evaluates the radial Laplacian in closed form (combine with UPDES_JET_VAL if c0 != 0) */
+#define UPDES_JET_ISO_LAPLACIAN 8
 int updes_assemble_rows(int rbf_kind, double rbf_param, int N, int M, const double *centres,
                         const UpdesRows *rows, int64_t row0, int64_t nrows, int jet_mask,
                         double *out, int64_t ld, void *stream);
@@ -120,6 +123,35 @@ int updes_dgemm_sub(UpdesLU *handle, double *K, int64_t rc, int64_t cc, int64_t 
                     int64_t rb, int64_t cb, int64_t m, int64_t n, int64_t k, void *stream);
 int updes_lu_panel(UpdesLU *handle, double *K, int64_t r0, int64_t nc, int32_t *ipiv,
                    int32_t *info, void *stream);
+
+/* ---- multi-GPU building blocks (column-block-cyclic LU, one process per GPU) ----------------------
+ * The local matrix (all n rows, this rank's column blocks) is slot 0 of the handle
+ * (updes_lu_create(n, ld_local) + updes_lu_bind(h, 0, ...)); panels received from other ranks live in
+ * auxiliary buffers bound to slots 1..3.  Pivot indices are global row numbers.  The host driver
+ * (updes_b200/distributed.py) strings these together with NCCL broadcasts of the panels.
+ */
+int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t ld);
+/* cap the persistent GEMM grid (0 = one CTA per SM) so NCCL kernels can run beside the update */
+int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
+/* LU of the tall panel rows [r0, rows) x columns [c0, c0+nc) of `slot`; interchanges are applied to
+ * the panel columns only; ipiv[r0 .. r0+nc) receives the pivots. */
+int updes_lu_panel_factor(UpdesLU *handle, int slot, int64_t r0, int64_t c0, int64_t nc, int32_t *ipiv,
+                          int32_t *info, void *stream);
+/* apply interchanges k0+t <-> ipiv[k0+t], t < npiv, to columns [c_lo, c_hi) of `slot` */
+int updes_lu_apply_swaps(UpdesLU *handle, int slot, int64_t c_lo, int64_t c_hi, int64_t k0, int64_t npiv,
+                         const int32_t *ipiv, void *stream);
+/* B <- L^-1 B: L unit-lower n1 x n1 at (rl, cl) of slot_l, B n1 x ncols at (rb, cb) of slot_b */
+int updes_lu_trsm(UpdesLU *handle, int slot_l, int64_t rl, int64_t cl, int64_t n1, int slot_b, int64_t rb,
+                  int64_t cb, int64_t ncols, void *stream);
+/* C -= A B with A (m x k) in slot_a, B (k x n) in slot_b, C (m x n) in slot_c */
+int updes_lu_gemm(UpdesLU *handle, int slot_a, int64_t ra, int64_t ca, int slot_b, int64_t rb, int64_t cb,
+                  int slot_c, int64_t rc, int64_t cc, int64_t m, int64_t n, int64_t k, void *stream);
+/* solves: row permutation from a complete pivot list; gather X = B[perm]; substitution restricted
+ * to one column block whose diagonal sits at rows [r0, r0+width), columns [c0, c0+width) of `slot` */
+int updes_lu_set_pivots(UpdesLU *handle, const int32_t *ipiv, void *stream);
+int updes_lu_permute_rhs(UpdesLU *handle, const double *B, int64_t ldb, int nrhs, double *X, void *stream);
+int updes_tri_block_sweep(UpdesLU *handle, int slot, int upper, int64_t r0, int64_t c0, int64_t width,
+                          double *X, int nrhs, void *stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char *updes_b200_version(void);

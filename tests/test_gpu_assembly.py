@@ -48,6 +48,23 @@ def test_jet_mask_specialisations(oracle, mask_cols):
         assert rel_err_rowscaled(got, want) <= 1e-12
 
 
+@pytest.mark.parametrize("kind,param", KERNELS)
+def test_isotropic_laplacian_fast_path(oracle, kind, param):
+    """c0*phi + c3*(phi_xx + phi_yy) rows take the closed-form radial-Laplacian kernel (Laplace, Helmholtz)."""
+    cloud = u.SquareCloud(Nx=19, Ny=23, facet_types=CONFIG1_FACETS, noise_key=9)
+    rng = np.random.default_rng(4)
+    for with_val in (False, True):
+        coef = np.zeros((cloud.Ni, 5))
+        coef[:, 3] = coef[:, 4] = rng.normal(size=cloud.Ni)
+        if with_val:
+            coef[:, 0] = rng.normal(size=cloud.Ni)
+        table = asm.build_operator_rows(cloud, coef)
+        assert table.masks()[0] & asm.JET_ISO
+        got = _assemble_K(cloud, kind, param, 3, coef)
+        want = oracle.assemble_K(cloud, kind, param, 3, coef)
+        assert rel_err_rowscaled(got, want) <= 1e-12
+
+
 def test_config2_periodic_rows(oracle):
     """35x35 periodic cloud of demos/Advection/01 (two periodic groups), adv-diff coefficients."""
     cloud = u.SquareCloud(Nx=35, Ny=35, facet_types=CONFIG2_FACETS, noise_key=7)

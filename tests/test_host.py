@@ -163,7 +163,7 @@ def test_row_descriptors_periodic_layout():
     f0 = v0 + half
     assert np.array_equal(t.p1[f0], v0) and np.all(t.cphi1[f0, 0] == 0) and np.all(t.cphi1[v0, 0] == 1) and np.all(t.cphi2[v0, 0] == -1)
     assert np.array_equal(t.skip[:Ni], np.arange(Ni))
-    assert t.masks() == (asm.JET_HESS | asm.JET_GRAD, asm.JET_VAL | asm.JET_GRAD)
+    assert t.masks() == (asm.JET_ISO, asm.JET_VAL | asm.JET_GRAD)
 
 
 def test_c_abi_exports_every_declared_symbol():

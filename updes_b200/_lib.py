@@ -35,6 +35,15 @@ SIGNATURES = {
     "updes_lu_solve": (_I32, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
     "updes_dgemm_sub": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "updes_lu_panel": (_I32, [_VP, _VP, _I64, _I64, _VP, _VP, _VP]),
+    "updes_lu_bind": (_I32, [_VP, _I32, _VP, _I64, _I64]),
+    "updes_lu_set_gemm_ctas": (_I32, [_VP, _I32]),
+    "updes_lu_panel_factor": (_I32, [_VP, _I32, _I64, _I64, _I64, _VP, _VP, _VP]),
+    "updes_lu_apply_swaps": (_I32, [_VP, _I32, _I64, _I64, _I64, _I64, _VP, _VP]),
+    "updes_lu_trsm": (_I32, [_VP, _I32, _I64, _I64, _I64, _I32, _I64, _I64, _I64, _VP]),
+    "updes_lu_gemm": (_I32, [_VP, _I32, _I64, _I64, _I32, _I64, _I64, _I32, _I64, _I64, _I64, _I64, _I64, _VP]),
+    "updes_lu_set_pivots": (_I32, [_VP, _VP, _VP]),
+    "updes_lu_permute_rhs": (_I32, [_VP, _VP, _I64, _I32, _VP, _VP]),
+    "updes_tri_block_sweep": (_I32, [_VP, _I32, _I32, _I64, _I64, _I64, _VP, _I32, _VP]),
     "updes_b200_version": (ctypes.c_char_p, []),
     "updes_launch_count": (_I64, []),
     "updes_profile_enable": (_I32, [_I32]),

@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 from .rbf import RBF_CODES
 
-JET_VAL, JET_GRAD, JET_HESS = 1, 2, 4
+JET_VAL, JET_GRAD, JET_HESS, JET_ISO = 1, 2, 4, 8
 
 
 def padded_ld(n: int) -> int:
@@ -30,15 +30,15 @@ def padded_ld(n: int) -> int:
 
 
 def _mask_of(coef: np.ndarray) -> int:
+    """Which parts of the jet a block of coefficient rows uses (kernel specialisation)."""
     if coef.size == 0:
         return JET_VAL
-    m = 0
-    if np.any(coef[:, 0] != 0):
-        m |= JET_VAL
-    if np.any(coef[:, 1:3] != 0):
-        m |= JET_GRAD
-    if np.any(coef[:, 3:5] != 0):
-        m |= JET_HESS | JET_GRAD
+    has_val = bool(np.any(coef[:, 0] != 0))
+    has_grad = bool(np.any(coef[:, 1:3] != 0))
+    has_hess = bool(np.any(coef[:, 3:5] != 0))
+    if has_hess and not has_grad and np.array_equal(coef[:, 3], coef[:, 4]):
+        return JET_ISO | (JET_VAL if has_val else 0)      # c0 phi + c3 lap(phi): closed-form radial Laplacian
+    m = (JET_VAL if has_val else 0) | (JET_GRAD if has_grad else 0) | ((JET_HESS | JET_GRAD) if has_hess else 0)
     return m or JET_VAL
 
 

@@ -149,6 +149,12 @@ __global__ void assemble_pt_rows_kernel(PtParams P) {
 template <int KIND>
 static int launch_phi(int mask, const AsmParams &P, cudaStream_t st) {
   dim3 grid((unsigned)((P.ncols + ASM_TC - 1) / ASM_TC), (unsigned)((P.nrows + ASM_TR - 1) / ASM_TR));
+  if (mask & JET_ISO) {
+    if (mask & JET_VAL) assemble_phi_kernel<KIND, JET_ISO | JET_VAL><<<grid, ASM_THREADS, 0, st>>>(P);
+    else assemble_phi_kernel<KIND, JET_ISO><<<grid, ASM_THREADS, 0, st>>>(P);
+    UPDES_LAUNCH_CHECK();
+    return 0;
+  }
   switch (mask & 7) {
     case 1: assemble_phi_kernel<KIND, 1><<<grid, ASM_THREADS, 0, st>>>(P); break;
     case 2: assemble_phi_kernel<KIND, 2><<<grid, ASM_THREADS, 0, st>>>(P); break;
@@ -172,8 +178,9 @@ static int assemble_block_impl(int kind, double param, int N, int M, const doubl
   if (!out) return -12;
   if (ld < ncols || (ld & 1)) return -13;
   if (nrows == 0 || ncols == 0) return 0;
-  if ((jet_mask & 7) == 0) jet_mask = 7;
-  if (jet_mask & JET_H) jet_mask |= JET_G;   // second derivatives carry the g term
+  if ((jet_mask & 15) == 0) jet_mask = 7;
+  if (jet_mask & JET_ISO) jet_mask &= (JET_ISO | JET_VAL);
+  else if (jet_mask & JET_H) jet_mask |= JET_G;   // second derivatives carry the g term
 
   const long long rc_end = row0 + nrows < N ? row0 + nrows : N;   // collocation rows [row0, rc_end)
   const long long cphi_end = col0 + ncols < N ? col0 + ncols : N;  // rbf columns [col0, cphi_end)

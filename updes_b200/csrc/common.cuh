@@ -38,11 +38,29 @@ void prof_end(cudaStream_t st);
 constexpr int JET_VAL = 1;   // phi needed
 constexpr int JET_G = 2;     // first derivatives (and/or the g part of second derivatives) needed
 constexpr int JET_H = 4;     // second derivatives needed
+constexpr int JET_ISO = 8;   // rows only use c0*phi + c3*(phi_xx + phi_yy): no gradient term, c3 == c4
+
+__device__ __forceinline__ bool is_zero_bits(double s) { return __double_as_longlong(s) == 0ll; }   // s >= 0 here
 
 __device__ __forceinline__ double ipow_u(double x, int e) {
   double v = 1.0;
   for (int k = 0; k < e; k++) v *= x;
   return v;
+}
+
+// 1/sqrt(s) in FP64 from the FP32 SFU estimate plus one third-order (Halley) correction:
+// 23 bits -> ~69 bits before rounding, about 1 ulp, in 5 FP64 operations instead of the ~12 of
+// rsqrt().  Falls back to rsqrt() outside the float range.
+__device__ __forceinline__ double fast_rsqrt(double s) {
+  // range test on the exponent bits (integer pipe, keeps the FP64 pipe for arithmetic):
+  // 2^-100 <= s < 2^100, which also excludes 0, negatives, inf and NaN
+  const unsigned int hi = (unsigned int)__double2hiint(s);
+  if (hi - 0x39B00000u >= 0x0C800000u) return rsqrt(s);
+  const double y = (double)rsqrtf((float)s);
+  const double t = s * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(y, q, y);
 }
 
 // Radial triple of a kernel as a function of s = r^2 > 0:
@@ -54,7 +72,7 @@ __device__ __forceinline__ void radial(double s, int ip, double e2, double &phi,
   if (KIND == UPDES_RBF_POLYHARMONIC) {
     // phi = r^p, p = 2a+1:  g = p r^(p-2),  h = p (p-2) r^(p-4)
     const int p = 2 * ip + 1;
-    const double rs = rsqrt(s);
+    const double rs = fast_rsqrt(s);
     double base;                       // r^(p-4)
     if (p >= 5) base = ipow_u(s, (p - 5) >> 1) * (s * rs);
     else if (p == 3) base = rs;
@@ -97,6 +115,26 @@ __device__ __forceinline__ void radial(double s, int ip, double e2, double &phi,
   }
 }
 
+// Radial Laplacian  lap(r) = phi'' + phi'/r = 2 g + h s  in closed form (2-D), with phi.
+template <int KIND>
+__device__ __forceinline__ void radial_lap(double s, int ip, double e2, double &phi, double &lap) {
+  if (KIND == UPDES_RBF_POLYHARMONIC) {
+    const int p = 2 * ip + 1;                 // lap = p^2 r^(p-2)
+    const double rs = fast_rsqrt(s);
+    const double r = s * rs;
+    double rp2;                               // r^(p-2)
+    if (p == 3) rp2 = r;
+    else if (p == 1) rp2 = rs;
+    else rp2 = ipow_u(s, (p - 3) >> 1) * r;
+    lap = (double)(p * p) * rp2;
+    phi = rp2 * s;
+  } else {
+    double g, h;
+    radial<KIND>(s, ip, e2, phi, g, h);
+    lap = fma(h, s, 2.0 * g);
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ double phi_at_zero() {
   return (KIND == UPDES_RBF_POLYHARMONIC || KIND == UPDES_RBF_THIN_PLATE) ? 0.0 : 1.0;
@@ -114,6 +152,13 @@ __device__ __forceinline__ double entry_one_point(const RowPoint &rp, double cx,
   const double dx = rp.x - cx, dy = rp.y - cy;
   const double dx2 = dx * dx, dy2 = dy * dy;
   const double s = dx2 + dy2;
+  if (MASK & JET_ISO) {
+    double phi, lap;
+    radial_lap<KIND>(s, ip, e2, phi, lap);
+    double v = rp.c3 * lap;
+    if (MASK & JET_VAL) v = fma(rp.c0, phi, v);
+    return is_zero_bits(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
+  }
   double phi, g, h;
   radial<KIND>(s, ip, e2, phi, g, h);
   double v = 0.0;
@@ -121,7 +166,7 @@ __device__ __forceinline__ double entry_one_point(const RowPoint &rp, double cx,
   if (MASK & JET_G) v = fma(g, fma(rp.c1, dx, fma(rp.c2, dy, rp.c34)), v);
   if (MASK & JET_VAL) v = fma(rp.c0, phi, v);
   // r == 0: derivatives -> 0 (nan_to_num), value -> phi(0)
-  return (s == 0.0) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
+  return is_zero_bits(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
 }
 
 // jet of monomial id (utils.py:92-134) at (x, y): value, d/dx, d/dy, d2/dx2, d2/dy2

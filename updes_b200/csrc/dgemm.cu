@@ -26,8 +26,8 @@ constexpr int GEMM_CONSUMERS = 8;
 constexpr int GEMM_THREADS = GEMM_CONSUMERS * 32;
 
 struct GemmParams {
-  double *C;           // matrix base
-  long long ld;
+  double *C;           // base of the buffer holding C
+  long long ld;        // its leading dimension
   long long rc, cc;    // C block origin
   long long ra, ca;    // A block origin (m x k)
   long long rb, cb;    // B block origin (k x n)
@@ -258,40 +258,40 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int lu_bind(UpdesLU *h, const double *K) {
-  if (h->bound == K) return 0;
+int lu_bind_view(UpdesLU *h, int slot, const double *ptr, int64_t rows, int64_t ld_) {
+  if (slot < 0 || slot >= UPDES_MAX_VIEWS) return -2;
+  MatView &V = h->view[slot];
+  if (V.ptr == ptr && V.rows == rows && V.ld == ld_) return 0;
+  if (!ptr || rows <= 0 || ld_ < 16 || (ld_ % 16) || (((uintptr_t)ptr) & 127)) return -3;
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
-  const cuuint64_t ld = (cuuint64_t)h->ld, n = (cuuint64_t)h->n;
+  const cuuint64_t ld = (cuuint64_t)ld_, n = (cuuint64_t)rows;
+  cuuint64_t dims[2] = {ld, n};
+  cuuint64_t strides[1] = {ld * 8};
+  cuuint32_t estr[2] = {1, 1};
   {
-    // A operand: dims (columns, rows); box 16 columns x 128 rows
-    cuuint64_t dims[2] = {ld, n};
-    cuuint64_t strides[1] = {ld * 8};
+    // left operand: box 16 columns (k) x 128 rows
     cuuint32_t box[2] = {GEMM_BK, GEMM_BM};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&h->mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)K, dims, strides, box, estr,
+    CUresult r = enc(&V.mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   }
   {
-    // B operand: box 16 columns x 16 k-rows; a BN-wide tile is BN/16 such boxes laid out
+    // right operand: box 16 columns x 16 k-rows; a BN-wide tile is BN/16 such boxes laid out
     // [column group][k][16 columns], which keeps the k rows 128 B apart (conflict-free LDS.64)
-    cuuint64_t dims[2] = {ld, n};
-    cuuint64_t strides[1] = {ld * 8};
     cuuint32_t box[2] = {16, GEMM_BK};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&h->mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)K, dims, strides, box, estr,
+    CUresult r = enc(&V.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   }
-  h->bound = K;
+  V.ptr = const_cast<double *>(ptr); V.rows = rows; V.ld = ld_;
   return 0;
 }
 
 template <int BN>
-static int launch_gemm(UpdesLU *h, const GemmParams &P, cudaStream_t st) {
+static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const GemmParams &P, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -300,26 +300,27 @@ static int launch_gemm(UpdesLU *h, const GemmParams &P, cudaStream_t st) {
     attr_set = true;
   }
   const long long tiles = ((P.m + GEMM_BM - 1) / GEMM_BM) * ((P.n + BN - 1) / BN);
-  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  const int cap = (h->gemm_ctas > 0 && h->gemm_ctas < h->num_sms) ? h->gemm_ctas : h->num_sms;
+  const int grid = (int)(tiles < cap ? tiles : cap);
   prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
-  dgemm_sub_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(h->mapA, h->mapB, P);
+  dgemm_sub_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, P);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
 }
 
-int dgemm_sub(UpdesLU *h, double *K, int64_t rc, int64_t cc, int64_t ra, int64_t ca, int64_t rb, int64_t cb,
-              int64_t m, int64_t n, int64_t k, cudaStream_t st) {
+int dgemm_sub(UpdesLU *h, int va, int64_t ra, int64_t ca, int vb, int64_t rb, int64_t cb, int vc, int64_t rc,
+              int64_t cc, int64_t m, int64_t n, int64_t k, cudaStream_t st) {
   if (m <= 0 || n <= 0 || k <= 0) return 0;
   if (k % GEMM_BK) return -11;
-  if ((cc & 1) || (cb & 15) || (ca & 1)) return -4;
-  int rc_ = lu_bind(h, K);
-  if (rc_) return rc_;
+  if (cc & 1) return -4;   // 16-byte C accesses; TMA boxes may start at any column
+  const MatView &VA = h->view[va], &VB = h->view[vb], &VC = h->view[vc];
+  if (!VA.ptr || !VB.ptr || !VC.ptr) return -2;
   GemmParams P;
-  P.C = K; P.ld = h->ld; P.rc = rc; P.cc = cc; P.ra = ra; P.ca = ca; P.rb = rb; P.cb = cb; P.m = m; P.n = n; P.k = k;
-  if (n <= 32) return launch_gemm<32>(h, P, st);
-  if (n <= 64) return launch_gemm<64>(h, P, st);
-  return launch_gemm<128>(h, P, st);
+  P.C = VC.ptr; P.ld = VC.ld; P.rc = rc; P.cc = cc; P.ra = ra; P.ca = ca; P.rb = rb; P.cb = cb; P.m = m; P.n = n; P.k = k;
+  if (n <= 32) return launch_gemm<32>(h, VA, VB, P, st);
+  if (n <= 64) return launch_gemm<64>(h, VA, VB, P, st);
+  return launch_gemm<128>(h, VA, VB, P, st);
 }
 
 }  // namespace updes
@@ -328,5 +329,23 @@ extern "C" int updes_dgemm_sub(UpdesLU *handle, double *K, int64_t rc, int64_t c
                                int64_t rb, int64_t cb, int64_t m, int64_t n, int64_t k, void *stream) {
   if (!handle) return -1;
   if (!K) return -2;
-  return updes::dgemm_sub(handle, K, rc, cc, ra, ca, rb, cb, m, n, k, (cudaStream_t)stream);
+  int rc_ = updes::lu_bind_view(handle, 0, K, handle->n, handle->ld);
+  if (rc_) return rc_;
+  return updes::dgemm_sub(handle, 0, ra, ca, 0, rb, cb, 0, rc, cc, m, n, k, (cudaStream_t)stream);
+}
+
+extern "C" int updes_lu_gemm(UpdesLU *handle, int slot_a, int64_t ra, int64_t ca, int slot_b, int64_t rb, int64_t cb,
+                             int slot_c, int64_t rc, int64_t cc, int64_t m, int64_t n, int64_t k, void *stream) {
+  if (!handle) return -1;
+  if (slot_a < 0 || slot_a >= UPDES_MAX_VIEWS) return -2;
+  if (slot_b < 0 || slot_b >= UPDES_MAX_VIEWS) return -5;
+  if (slot_c < 0 || slot_c >= UPDES_MAX_VIEWS) return -8;
+  return updes::dgemm_sub(handle, slot_a, ra, ca, slot_b, rb, cb, slot_c, rc, cc, m, n, k, (cudaStream_t)stream);
+}
+
+extern "C" int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas) {
+  if (!handle) return -1;
+  if (ctas < 0) return -2;
+  handle->gemm_ctas = ctas;
+  return 0;
 }

@@ -5,13 +5,22 @@
 #include <stdint.h>
 #include "common.cuh"
 
+// A row-major buffer the LU kernels can address: the (local) matrix itself (slot 0) or an
+// auxiliary panel buffer (slots 1..3) that holds a broadcast panel on the multi-GPU path.
+struct MatView {
+  double *ptr = nullptr;
+  int64_t ld = 0, rows = 0;
+  CUtensorMap mapA;        // 2D, box {16 k, 128 rows}, 128B swizzle: left (L) operand tiles
+  CUtensorMap mapB;        // 2D, box {16 cols, 16 k-rows}, 128B swizzle: right (U) operand tiles
+};
+
+constexpr int UPDES_MAX_VIEWS = 4;
+
 struct UpdesLU {
-  int64_t n = 0, ld = 0;
+  int64_t n = 0, ld = 0;   // rows and leading dimension of slot 0
   int num_sms = 148;
-  // TMA descriptors over the whole matrix, rebuilt when the bound pointer changes
-  const double *bound = nullptr;
-  CUtensorMap mapA;        // 2D, box {16 k, 128 rows}, 128B swizzle: L operand tiles
-  CUtensorMap mapB;        // 2D, box {16 cols, 16 k-rows}, 128B swizzle: U operand tiles
+  int gemm_ctas = 0;       // 0 = one CTA per SM; smaller leaves SMs free for concurrent NCCL kernels
+  MatView view[UPDES_MAX_VIEWS];
   // device workspace of the panel kernel
   double *cand = nullptr;          // [2][num_sms][PANEL_W] candidate pivot rows
   double *top = nullptr;           // [2][PANEL_W] row currently at the diagonal position
@@ -19,7 +28,7 @@ struct UpdesLU {
   int32_t *candrow = nullptr;      // [2][num_sms]
   unsigned int *barrier = nullptr; // grid barrier counter (monotonic)
   unsigned int barrier_count = 0;  // host mirror of the counter after all enqueued panels
-  int32_t *perm = nullptr;         // [n] scratch for solves
+  int32_t *perm = nullptr;         // [n] row permutation of the last factorisation (for solves)
   double *xbuf = nullptr;          // solve scratch
 };
 
@@ -27,14 +36,22 @@ namespace updes {
 
 constexpr int PANEL_W = 32;   // widest base panel
 
-int lu_bind(UpdesLU *h, const double *K);
-int dgemm_sub(UpdesLU *h, double *K, int64_t rc, int64_t cc, int64_t ra, int64_t ca, int64_t rb, int64_t cb,
-              int64_t m, int64_t n, int64_t k, cudaStream_t st);
+int lu_bind_view(UpdesLU *h, int slot, const double *ptr, int64_t rows, int64_t ld);
+// C[rc.., cc..] -= A[ra.., ca..] (m x k, view va) * B[rb.., cb..] (k x n, view vb); C in view vc
+int dgemm_sub(UpdesLU *h, int va, int64_t ra, int64_t ca, int vb, int64_t rb, int64_t cb, int vc, int64_t rc,
+              int64_t cc, int64_t m, int64_t n, int64_t k, cudaStream_t st);
 int panel_width_for(const UpdesLU *h, int64_t m);
-int lu_panel_base(UpdesLU *h, double *K, int64_t r0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st);
-int swap_rows(UpdesLU *h, double *K, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
+// base panel: rows [r0, rows) x columns [c0, c0+jb) of view v; pivots -> ipiv[r0 .. r0+jb)
+int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st);
+int swap_rows(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
               cudaStream_t st);
-int trsm_unit_lower(UpdesLU *h, double *K, int64_t r0, int64_t n1, int64_t c0, int64_t ncols, cudaStream_t st);
-int lu_recursive(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, int32_t *info, cudaStream_t st);
+// B <- L^-1 B, L = unit-lower n1 x n1 at (rl, cl) of view vl, B = n1 x ncols at (rb, cb) of view vb
+int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int vb, int64_t rb, int64_t cb,
+                    int64_t ncols, cudaStream_t st);
+// recursive LU of rows [r0, rows) x columns [c0, c0+nc) of view v; interchanges are applied to the
+// columns [swap_lo, swap_hi) of the same view (the panel itself included)
+int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t swap_lo, int64_t swap_hi,
+                 int32_t *ipiv, int32_t *info, cudaStream_t st);
+int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st);
 
 }  // namespace updes

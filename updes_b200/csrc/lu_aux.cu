@@ -34,16 +34,19 @@ __global__ void __launch_bounds__(SWAP_THREADS) swap_rows_kernel(double *K, long
   }
 }
 
-int swap_rows(UpdesLU *h, double *K, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
+int swap_rows(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
               cudaStream_t st) {
   if (ncols <= 0 || npiv <= 0) return 0;
+  double *K = h->view[v].ptr;
+  const long long ld = h->view[v].ld;
+  if (!K) return -2;
   if (c0 & 1) return -3;
   for (int64_t t0 = 0; t0 < npiv; t0 += SWAP_MAX_PIV) {
     const int np = (int)((npiv - t0) < SWAP_MAX_PIV ? (npiv - t0) : SWAP_MAX_PIV);
     const long long pairs = (ncols + 1) / 2;
     prof_begin(PROF_SWAP, 32.0 * (double)ncols * np, st);
     swap_rows_kernel<<<(unsigned)((pairs + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
-        K, h->ld, c0, ncols, k0 + t0, np, ipiv);
+        K, ld, c0, ncols, k0 + t0, np, ipiv);
     prof_end(st);
     UPDES_LAUNCH_CHECK();
   }
@@ -55,19 +58,20 @@ int swap_rows(UpdesLU *h, double *K, int64_t c0, int64_t ncols, int64_t k0, int6
 // One thread per column of B: the NB values of the column live in registers, L is broadcast from
 // shared memory; loads/stores are coalesced across the threads of a warp (adjacent columns).
 template <int NB>
-__global__ void __launch_bounds__(128) trsm_base_kernel(double *K, long long ld, long long r0, long long c0,
+__global__ void __launch_bounds__(128) trsm_base_kernel(const double *Lm, long long ldl, long long rl, long long cl,
+                                                        double *B, long long ldb, long long rb, long long cb,
                                                         long long ncols) {
   __shared__ double L[NB][NB + 1];
   for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
     const int i = t / NB, j = t % NB;
-    L[i][j] = K[(r0 + i) * ld + r0 + j];
+    L[i][j] = Lm[(rl + i) * ldl + cl + j];
   }
   __syncthreads();
-  const long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c0 + ncols) return;
+  const long long c = cb + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cb + ncols) return;
   double x[NB];
 #pragma unroll
-  for (int i = 0; i < NB; i++) x[i] = K[(r0 + i) * ld + c];
+  for (int i = 0; i < NB; i++) x[i] = B[(rb + i) * ldb + c];
 #pragma unroll
   for (int i = 1; i < NB; i++) {
     double v = x[i];
@@ -76,16 +80,17 @@ __global__ void __launch_bounds__(128) trsm_base_kernel(double *K, long long ld,
     x[i] = v;
   }
 #pragma unroll
-  for (int i = 1; i < NB; i++) K[(r0 + i) * ld + c] = x[i];
+  for (int i = 1; i < NB; i++) B[(rb + i) * ldb + c] = x[i];
 }
 
-static int trsm_base(UpdesLU *h, double *K, int64_t r0, int nb, int64_t c0, int64_t ncols, cudaStream_t st) {
+static int trsm_base(UpdesLU *h, int vl, int64_t rl, int64_t cl, int nb, int vb, int64_t rb, int64_t cb,
+                     int64_t ncols, cudaStream_t st) {
+  const MatView &VL = h->view[vl], &VB = h->view[vb];
   const unsigned grid = (unsigned)((ncols + 127) / 128);
+  if (nb != 32 && nb != 16) return -4;
   prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
-  if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
-  else if (nb == 16) trsm_base_kernel<16><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
-  else if (nb == 8) trsm_base_kernel<8><<<grid, 128, 0, st>>>(K, h->ld, r0, c0, ncols);
-  else return -4;
+  if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  else trsm_base_kernel<16><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
@@ -93,15 +98,18 @@ static int trsm_base(UpdesLU *h, double *K, int64_t r0, int nb, int64_t c0, int6
 
 // Recursive blocked solve: split L11, solve the top half, rank-update the bottom half with the
 // DMMA GEMM, solve the bottom half.  n1 is a multiple of the base width.
-int trsm_unit_lower(UpdesLU *h, double *K, int64_t r0, int64_t n1, int64_t c0, int64_t ncols, cudaStream_t st) {
+int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int vb, int64_t rb, int64_t cb,
+                    int64_t ncols, cudaStream_t st) {
   if (n1 <= 0 || ncols <= 0) return 0;
-  if (n1 <= 32) return trsm_base(h, K, r0, (int)n1, c0, ncols, st);
-  int64_t hlf = (n1 / 2 + 31) / 32 * 32;
-  int rc = trsm_unit_lower(h, K, r0, hlf, c0, ncols, st);
+  if (!h->view[vl].ptr || !h->view[vb].ptr) return -2;
+  if (n1 <= 32) return trsm_base(h, vl, rl, cl, (int)n1, vb, rb, cb, ncols, st);
+  const int64_t hlf = (n1 / 2 + 31) / 32 * 32;
+  int rc = trsm_unit_lower(h, vl, rl, cl, hlf, vb, rb, cb, ncols, st);
   if (rc) return rc;
-  rc = dgemm_sub(h, K, r0 + hlf, c0, r0 + hlf, r0, r0, c0, n1 - hlf, ncols, hlf, st);
+  // B[hlf:, :] -= L[hlf:, :hlf] * B[:hlf, :]
+  rc = dgemm_sub(h, vl, rl + hlf, cl, vb, rb, cb, vb, rb + hlf, cb, n1 - hlf, ncols, hlf, st);
   if (rc) return rc;
-  return trsm_unit_lower(h, K, r0 + hlf, n1 - hlf, c0, ncols, st);
+  return trsm_unit_lower(h, vl, rl + hlf, cl + hlf, n1 - hlf, vb, rb + hlf, cb, ncols, st);
 }
 
 // ---- pivots -> permutation ------------------------------------------------------------------------

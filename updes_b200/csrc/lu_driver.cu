@@ -7,37 +7,40 @@
 // factored recursively, the right half gets U12 = L11^-1 A12 (recursive triangular solve) and the
 // Schur update A22 -= L21 U12 (DMMA GEMM), then the right half is factored recursively.  All
 // O(n^3) work lands in the GEMM with the largest possible inner dimension.  Row interchanges are
-// applied to the rest of the matrix right after each base panel (32 pivots at a time), which keeps
-// every interchange kernel short and fully coalesced in the row-major layout.
+// applied to the rest of the swap range right after each base panel (32 pivots at a time), which
+// keeps every interchange kernel short and fully coalesced in the row-major layout.
+//
+// The same routine factors (a) the whole matrix on one GPU (swap range = all columns) and (b) one
+// column panel of a column-block-cyclic local matrix on the multi-GPU path (swap range = the panel
+// only; the other columns, local and remote, get the interchanges when the panel is applied).
 #include "lu.cuh"
 
 namespace updes {
 
-int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st);
-
-int lu_recursive(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, int32_t *info, cudaStream_t st) {
+int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t swap_lo, int64_t swap_hi,
+                 int32_t *ipiv, int32_t *info, cudaStream_t st) {
   if (nc <= 0) return 0;
-  const int64_t n = h->n;
-  const int W = panel_width_for(h, n - r0);
+  const int64_t rows = h->view[v].rows;
+  const int W = panel_width_for(h, rows - r0);
   if (W < 16) return -2;   // panel taller than the register-resident kernel supports
   if (nc <= W) {
-    int rc = lu_panel_base(h, K, r0, (int)nc, ipiv, info, st);
+    int rc = lu_panel_base(h, v, r0, c0, (int)nc, ipiv, info, st);
     if (rc) return rc;
-    rc = swap_rows(h, K, 0, r0, r0, nc, ipiv, st);
+    rc = swap_rows(h, v, swap_lo, c0 - swap_lo, r0, nc, ipiv, st);
     if (rc) return rc;
-    return swap_rows(h, K, r0 + nc, n - (r0 + nc), r0, nc, ipiv, st);
+    return swap_rows(h, v, c0 + nc, swap_hi - (c0 + nc), r0, nc, ipiv, st);
   }
   int64_t n1;
   if (nc <= 32) n1 = 16;
   else n1 = (nc / 2 + 31) / 32 * 32;
-  int rc = lu_recursive(h, K, r0, n1, ipiv, info, st);
+  int rc = lu_recursive(h, v, r0, c0, n1, swap_lo, swap_hi, ipiv, info, st);
   if (rc) return rc;
   const int64_t n2 = nc - n1;
-  rc = trsm_unit_lower(h, K, r0, n1, r0 + n1, n2, st);
+  rc = trsm_unit_lower(h, v, r0, c0, n1, v, r0, c0 + n1, n2, st);
   if (rc) return rc;
-  rc = dgemm_sub(h, K, r0 + n1, r0 + n1, r0 + n1, r0, r0, r0 + n1, n - (r0 + n1), n2, n1, st);
+  rc = dgemm_sub(h, v, r0 + n1, c0, v, r0, c0 + n1, v, r0 + n1, c0 + n1, rows - (r0 + n1), n2, n1, st);
   if (rc) return rc;
-  return lu_recursive(h, K, r0 + n1, n2, ipiv, info, st);
+  return lu_recursive(h, v, r0 + n1, c0 + n1, n2, swap_lo, swap_hi, ipiv, info, st);
 }
 
 }  // namespace updes
@@ -45,7 +48,7 @@ int lu_recursive(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, i
 extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   if (!handle) return -1;
   if (n <= 0 || n > 0x7fffffff) return -2;
-  if (ld < n || (ld % 16)) return -3;
+  if (ld < 16 || (ld % 16)) return -3;
   UpdesLU *h = new UpdesLU();
   h->n = n; h->ld = ld;
   int dev = 0;
@@ -76,16 +79,22 @@ extern "C" int updes_lu_destroy(UpdesLU *h) {
   return 0;
 }
 
+extern "C" int updes_lu_bind(UpdesLU *h, int slot, double *ptr, int64_t rows, int64_t ld) {
+  if (!h) return -1;
+  return updes::lu_bind_view(h, slot, ptr, rows, ld);
+}
+
 extern "C" int updes_lu_factor(UpdesLU *h, double *K, int32_t *ipiv, int32_t *info, void *stream) {
   if (!h) return -1;
   if (!K || (((uintptr_t)K) & 127)) return -2;   // rows must be whole 128-byte lines
   if (!ipiv) return -3;
   if (!info) return -4;
+  if (h->ld < h->n) return -1;
   cudaStream_t st = (cudaStream_t)stream;
   UPDES_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-  int rc = updes::lu_bind(h, K);
+  int rc = updes::lu_bind_view(h, 0, K, h->n, h->ld);
   if (rc) return rc;
-  rc = updes::lu_recursive(h, K, 0, h->n, ipiv, info, st);
+  rc = updes::lu_recursive(h, 0, 0, 0, h->n, 0, h->n, ipiv, info, st);
   if (rc) return rc;
   return updes::build_permutation(h, ipiv, st);
 }
@@ -94,8 +103,41 @@ extern "C" int updes_lu_panel(UpdesLU *h, double *K, int64_t r0, int64_t nc, int
                               void *stream) {
   if (!h) return -1;
   if (!K) return -2;
-  return updes::lu_panel_base(h, K, r0, (int)nc, ipiv, info, (cudaStream_t)stream);
+  int rc = updes::lu_bind_view(h, 0, K, h->n, h->ld);
+  if (rc) return rc;
+  return updes::lu_panel_base(h, 0, r0, r0, (int)nc, ipiv, info, (cudaStream_t)stream);
 }
 
-extern "C" const char *updes_b200_version(void) { return "updes_b200 0.1 (sm_100a)"; }
+// ---- building blocks of the distributed (column-block-cyclic) factorisation ------------------------
+extern "C" int updes_lu_panel_factor(UpdesLU *h, int slot, int64_t r0, int64_t c0, int64_t nc, int32_t *ipiv,
+                                     int32_t *info, void *stream) {
+  if (!h) return -1;
+  if (slot < 0 || slot >= UPDES_MAX_VIEWS || !h->view[slot].ptr) return -2;
+  if (r0 < 0 || r0 >= h->view[slot].rows) return -3;
+  if (c0 < 0 || (c0 & 1) || c0 + nc > h->view[slot].ld) return -4;
+  if (!ipiv) return -6;
+  if (!info) return -7;
+  return updes::lu_recursive(h, slot, r0, c0, nc, c0, c0 + nc, ipiv, info, (cudaStream_t)stream);
+}
+
+extern "C" int updes_lu_apply_swaps(UpdesLU *h, int slot, int64_t c_lo, int64_t c_hi, int64_t k0, int64_t npiv,
+                                    const int32_t *ipiv, void *stream) {
+  if (!h) return -1;
+  if (slot < 0 || slot >= UPDES_MAX_VIEWS || !h->view[slot].ptr) return -2;
+  if (c_lo < 0 || (c_lo & 1) || c_hi > h->view[slot].ld) return -3;
+  if (!ipiv) return -7;
+  return updes::swap_rows(h, slot, c_lo, c_hi - c_lo, k0, npiv, ipiv, (cudaStream_t)stream);
+}
+
+extern "C" int updes_lu_trsm(UpdesLU *h, int slot_l, int64_t rl, int64_t cl, int64_t n1, int slot_b, int64_t rb,
+                             int64_t cb, int64_t ncols, void *stream) {
+  if (!h) return -1;
+  if (slot_l < 0 || slot_l >= UPDES_MAX_VIEWS) return -2;
+  if (slot_b < 0 || slot_b >= UPDES_MAX_VIEWS) return -6;
+  if (n1 > 32 && (n1 % 32)) return -5;
+  if (n1 <= 32 && n1 != 32 && n1 != 16) return -5;
+  return updes::trsm_unit_lower(h, slot_l, rl, cl, n1, slot_b, rb, cb, ncols, (cudaStream_t)stream);
+}
+
+extern "C" const char *updes_b200_version(void) { return "updes_b200 0.2 (sm_100a)"; }
 extern "C" int64_t updes_launch_count(void) { return updes::g_launch_count; }

@@ -21,7 +21,7 @@ constexpr int PANEL_THREADS = 640;
 
 struct PanelParams {
   double *K;
-  long long ld, n, r0;
+  long long ld, n, r0, c0;   // panel = rows [r0, n) x columns [c0, c0+jb)
   int jb;              // columns in this panel (<= JB)
   int rows_per_cta;    // R
   int32_t *ipiv, *info;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
     const bool valid = li < P.rows_per_cta && row < P.n;
     myrow[q] = valid ? row : -1;
     if (valid) {
-      const double *src = P.K + row * P.ld + P.r0;
+      const double *src = P.K + row * P.ld + P.c0;
       if (jb == JB) {
 #pragma unroll
         for (int c = 0; c < JB; c += 2) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
 #pragma unroll
   for (int q = 0; q < RPT; q++) {
     if (myrow[q] < 0) continue;
-    double *dst = P.K + myrow[q] * P.ld + P.r0;
+    double *dst = P.K + myrow[q] * P.ld + P.c0;
     if (jb == JB) {
 #pragma unroll
       for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(a[q][c], a[q][c + 1]);
@@ -238,8 +238,11 @@ int panel_width_for(const UpdesLU *h, int64_t m) {
   return 0;
 }
 
-int lu_panel_base(UpdesLU *h, double *K, int64_t r0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st) {
-  const int64_t m = h->n - r0;
+int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st) {
+  const MatView &V = h->view[v];
+  if (!V.ptr) return -2;
+  if (c0 & 1) return -4;
+  const int64_t m = V.rows - r0;
   if (m <= 0 || jb <= 0) return 0;
   const int JBmax = panel_width_for(h, m);
   if (JBmax == 0) return -3;
@@ -256,7 +259,7 @@ int lu_panel_base(UpdesLU *h, double *K, int64_t r0, int jb, int32_t *ipiv, int3
   if (threads > PANEL_THREADS) return -3;
   if (R < jb && ctas > 1) return -3;
   PanelParams P;
-  P.K = K; P.ld = h->ld; P.n = h->n; P.r0 = r0; P.jb = jb; P.rows_per_cta = (int)R;
+  P.K = V.ptr; P.ld = V.ld; P.n = V.rows; P.r0 = r0; P.c0 = c0; P.jb = jb; P.rows_per_cta = (int)R;
   P.ipiv = ipiv; P.info = info; P.cand = h->cand; P.top = h->top; P.candval = h->candval; P.candrow = h->candrow;
   P.barrier = h->barrier; P.barrier_base = h->barrier_count; P.num_ctas = ctas;
   h->barrier_count += (unsigned int)ctas * (unsigned int)jb;

@@ -417,6 +417,60 @@ class _System:
         return self.K.numel() * 8
 
 
+def _dist_world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except Exception:
+        pass
+    return 1, 0
+
+
+def default_block_width(n, world):
+    """Column-block width of the multi-GPU layout: 1024 for large systems, smaller when the matrix
+    would otherwise have fewer than ~8 blocks per rank."""
+    nb = 1024
+    while nb > 64 and n // (nb * world) < 8:
+        nb //= 2
+    return nb
+
+
+class _DistSystem:
+    """The same system sharded column-block-cyclically over all ranks of the default process group
+    (updes_b200/distributed.py).  Every rank calls pde_solver with identical arguments."""
+
+    def __init__(self, cloud, kind, param, M, table, world, rank):
+        from .distributed import ColumnBlockCyclic, CudaBackend, DistributedLU
+        self.kind, self.param, self.M = kind, param, M
+        self.rows = _asm.DeviceRows(cloud, table)
+        self.n = cloud.N + M
+        self.layout = ColumnBlockCyclic(self.n, default_block_width(self.n, world), world)
+        self.be = CudaBackend(self.layout, rank, gemm_sms_reserved=8)
+        self.be.assemble(self.rows, kind, param, M)
+        self.dlu = DistributedLU(self.layout, rank, self.be).factor()
+        self.lu = self                       # zero_pivot() interface of LUFactorization
+        self.K = self.be.local
+
+    def zero_pivot(self):
+        import torch.distributed as dist
+        t = self.be.info.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def solve(self, rhs, refine=1):
+        torch = self.rows.torch
+        b = torch.as_tensor(rhs, dtype=torch.float64).to(self.be.device)
+        c = self.dlu.solve(rhs)
+        for _ in range(refine):
+            r = b - _asm.apply_rows(self.rows, self.kind, self.param, self.M, c.view(1, -1))[0]
+            c = c + self.dlu.solve(r)
+        return c
+
+    def nbytes(self):
+        return self.be.local.numel() * 8
+
+
 _CACHE: "OrderedDict[tuple, _System]" = OrderedDict()
 _CACHE_BYTES = 80 << 30
 
@@ -497,8 +551,12 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     betas = np.array([robin_coeffs[k] for k in sorted(robin_coeffs)], dtype=np.float64) if robin_coeffs else None
 
     key = ("K", id(cloud), kind, param, M, coef_phi.tobytes(), coef_pol.tobytes(), None if betas is None else betas.tobytes())
-    system = _cached_system(key, lambda: _System(cloud, kind, param, M,
-                                                 _asm.build_operator_rows(cloud, coef_phi, coef_pol, betas)))
+    world, rank = _dist_world()
+    table_fn = lambda: _asm.build_operator_rows(cloud, coef_phi, coef_pol, betas)
+    if world > 1:
+        system = _cached_system(key + (world,), lambda: _DistSystem(cloud, kind, param, M, table_fn(), world, rank))
+    else:
+        system = _cached_system(key, lambda: _System(cloud, kind, param, M, table_fn()))
     q = assemble_q(rhs_operator, boundary_conditions, cloud, rbf, M, rhs_args)
     coeffs_dev = system.solve(np.concatenate([q, np.zeros(M)]), refine=refine)
     if system.lu.zero_pivot():
