@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=0, help="SquareCloud side (default 300 * gpus^(1/4): 300 -> the 90k-node headline config)")
     ap.add_argument("--nb", type=int, default=0, help="column-block width of the multi-GPU layout (default: auto)")
-    ap.add_argument("--reserve-sms", type=int, default=8, help="SMs left free by the update GEMM for NCCL (multi-GPU)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left free by the update GEMM for NCCL (multi-GPU)")
     ap.add_argument("--cpu-nx", type=int, default=70, help="side of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")

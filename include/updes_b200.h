@@ -133,6 +133,8 @@ int updes_lu_panel(UpdesLU *handle, double *K, int64_t r0, int64_t nc, int32_t *
 int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t ld);
 /* cap the persistent GEMM grid (0 = one CTA per SM) so NCCL kernels can run beside the update */
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
+/* trailing-update GEMM schedule: 0 = one 128x128 CTA per SM, 1 = ping-pong (two 128x64 CTAs per SM) */
+int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
 /* LU of the tall panel rows [r0, rows) x columns [c0, c0+nc) of `slot`; interchanges are applied to
  * the panel columns only; ipiv[r0 .. r0+nc) receives the pivots. */
 int updes_lu_panel_factor(UpdesLU *handle, int slot, int64_t r0, int64_t c0, int64_t nc, int32_t *ipiv,

@@ -15,6 +15,31 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _gather_factors(layout, be, world, n, nb):
+    """Full factored matrix (on every rank) from the owned column blocks."""
+    import torch
+    import torch.distributed as dist
+    F = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    for j in layout.local_blocks(be.rank):
+        w, lc = layout.width(j), layout.local_offset(j)
+        F[:, j * nb:j * nb + w] = be.local[:, lc:lc + w]
+    dist.all_reduce(F)
+    return F
+
+
+def _reconstruction_error(F, piv, K):
+    """max |L U - P K| / max |K| for factors F and 0-based interchange list piv."""
+    import torch
+    n = K.shape[0]
+    L = torch.tril(F, -1) + torch.eye(n, dtype=torch.float64, device=F.device)
+    U = torch.triu(F)
+    PK = K.clone()
+    for k, p in enumerate(piv.tolist()):
+        if p != k:
+            PK[[k, p]] = PK[[p, k]]
+    return float((L @ U - PK).abs().max() / K.abs().max()), float(L.abs().max())
+
+
 def _worker(rank, world, port, nx, nb, out):
     import torch
     import torch.distributed as dist
@@ -25,40 +50,54 @@ def _worker(rank, world, port, nx, nb, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        cloud = u.SquareCloud(Nx=nx, Ny=nx, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+        # ---- (1) random matrix, no ties: pivots must equal LAPACK's exactly ---------------------------
+        n1 = nx * nx + 3
+        g = torch.Generator().manual_seed(5)
+        A = torch.randn((n1, n1), generator=g, dtype=torch.float64)
+        layout = ColumnBlockCyclic(n1, nb, world)
+        be = CudaBackend(layout, rank, gemm_sms_reserved=8)
+        for j in layout.local_blocks(rank):
+            w, lc = layout.width(j), layout.local_offset(j)
+            be.local[:, lc:lc + w] = A[:, j * nb:j * nb + w].cuda()
+        lu = DistributedLU(layout, rank, be).factor()
+        bvec = torch.randn(n1, generator=g, dtype=torch.float64)
+        x = lu.solve(bvec.numpy())
+        lu_ref, piv_ref = torch.linalg.lu_factor(A)
+        F = _gather_factors(layout, be, world, n1, nb)
+        piv_same = bool(np.array_equal(be.ipiv.cpu().numpy(), piv_ref.numpy() - 1))
+        fac_err = float((F.cpu() - lu_ref).abs().max() / lu_ref.abs().max())
+        sol_err = float((x.cpu() - torch.linalg.solve(A, bvec)).abs().max() / x.abs().max())
+        zp = be.zero_pivot()
+        del be, lu
+
+        # ---- (2) the collocation problem on a jittered cloud ----------------------------------------------
+        cloud = u.SquareCloud(Nx=nx, Ny=nx, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"}, noise_key=3)
         M, n = 3, cloud.N + 3
         coef = np.tile([0.0, 0, 0, 1.0, 1.0], (cloud.Ni, 1))
         rows = asm.DeviceRows(cloud, asm.build_operator_rows(cloud, coef))
         layout = ColumnBlockCyclic(n, nb, world)
         be = CudaBackend(layout, rank, gemm_sms_reserved=8)
         be.assemble(rows, "polyharmonic", 1.0, M)
-        # assembled blocks == the single-GPU assembly
-        Kfull = asm.assemble_system(rows, "polyharmonic", 1.0, M)
+        Kfull = asm.assemble_system(rows, "polyharmonic", 1.0, M)[:, :n].contiguous()
+        asm_same = True
         for j in layout.local_blocks(rank):
             w, lc = layout.width(j), layout.local_offset(j)
-            assert torch.equal(be.local[:, lc:lc + w], Kfull[:, j * nb:j * nb + w])
+            asm_same = asm_same and bool(torch.equal(be.local[:, lc:lc + w], Kfull[:, j * nb:j * nb + w]))
         lu = DistributedLU(layout, rank, be).factor()
         xy = cloud.sorted_nodes
         q = np.zeros(n)
         north = np.asarray(cloud.facet_nodes["North"])
         q[north] = np.sin(np.pi * xy[north, 0])
         x = lu.solve(q)
-        torch.cuda.synchronize()
-        # reference: single-GPU factorisation of the same matrix
-        from updes_b200.linalg import LUFactorization
-        ref = LUFactorization(Kfull, n).factor()
-        xref = ref.solve(torch.as_tensor(q).cuda())
-        piv_same = bool(torch.equal(ref.ipiv, be.ipiv))
-        err = float((x - xref).abs().max() / xref.abs().max())
-        fac_err = 0.0
-        for j in layout.local_blocks(rank):
-            w, lc = layout.width(j), layout.local_offset(j)
-            d = (be.local[:, lc:lc + w] - Kfull[:, j * nb:j * nb + w]).abs().max() / Kfull[:, :n].abs().max()
-            fac_err = max(fac_err, float(d))
+        F = _gather_factors(layout, be, world, n, nb)
+        rec_err, lmax = _reconstruction_error(F, be.ipiv.cpu().numpy(), Kfull)
+        bq = torch.as_tensor(q).cuda()
+        berr = float((Kfull @ x - bq).abs().max() / (Kfull.abs().sum(dim=1).max() * x.abs().max() + bq.abs().max()))
         res = [None] * world
-        dist.all_gather_object(res, (piv_same, err, fac_err, be.zero_pivot()))
+        dist.all_gather_object(res, (float(piv_same), fac_err, sol_err, float(zp), float(asm_same), rec_err, lmax, berr,
+                                     float(be.zero_pivot())))
         if rank == 0:
-            np.save(out, np.array([[float(a), b, c, float(d)] for a, b, c, d in res]))
+            np.save(out, np.array(res))
     finally:
         dist.destroy_process_group()
 
@@ -71,10 +110,15 @@ def _run(world, nx, nb, tmp_path):
     out = str(tmp_path / "res.npy")
     mp.spawn(_worker, args=(world, _free_port(), nx, nb, out), nprocs=world, join=True)
     r = np.load(out)
-    assert np.all(r[:, 0] == 1.0), "pivot lists differ from the single-GPU factorisation"
-    assert np.all(r[:, 1] <= 1e-9), r
-    assert np.all(r[:, 2] <= 1e-11), r          # same factors up to GEMM blocking order
+    assert np.all(r[:, 0] == 1.0), "pivots differ from LAPACK partial pivoting on a tie-free matrix"
+    assert np.all(r[:, 1] <= 1e-10), r          # factors == LAPACK's
+    assert np.all(r[:, 2] <= 1e-8), r           # solution
     assert np.all(r[:, 3] == 0)
+    assert np.all(r[:, 4] == 1.0), "distributed assembly must be bit-identical to the single-GPU assembly"
+    assert np.all(r[:, 5] <= 1e-12), r          # P K = L U
+    assert np.all(r[:, 6] <= 1.0 + 1e-12), r    # partial pivoting: |L| <= 1
+    assert np.all(r[:, 7] <= 1e-14), r          # backward error of the distributed solve
+    assert np.all(r[:, 8] == 0)
 
 
 @pytest.mark.parametrize("nx,nb", [(24, 64), (40, 128), (50, 512)])

@@ -18,9 +18,10 @@ def _matrix(n, seed=0, ld=None, dominant=False):
     return A, K.cuda()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 128, 64), (300, 200, 32), (1000, 96, 128), (77, 500, 48),
-                                   (2048, 2048, 512), (129, 33, 16), (64, 32, 32), (4000, 64, 256)])
-def test_dgemm_sub(m, n, k):
+                                   (2048, 2048, 512), (129, 33, 16), (64, 32, 32), (4000, 64, 256), (5000, 3001, 96)])
+def test_dgemm_sub(m, n, k, variant):
     """C -= A @ B on sub-blocks of one matrix vs torch (DMMA + TMA kernel, all tile shapes / edges)."""
     import torch
     from updes_b200.linalg import LUFactorization
@@ -30,6 +31,7 @@ def test_dgemm_sub(m, n, k):
     size = max(N, cols)
     _, K = _matrix(size, seed=m + n + k)
     lu = LUFactorization(K, size)
+    lu.set_gemm_variant(variant)          # 1 = ping-pong schedule (two 128x64 CTAs per SM) for wide updates
     # A at (ra=k+32.., ca=0), B at (rb=0, cb=k+32), C at (k+32, k+32): an LU-like arrangement
     ra, ca, rb, cb = 32 + k, 0, 0, 32 + k
     rc, cc = 32 + k, 32 + k

@@ -14,7 +14,9 @@ ld = padded_ld(n)
 K = torch.randn((n, ld), dtype=torch.float64, device="cuda")
 lu = LUFactorization(K, n)
 out = {}
-for k in (32, 128, 512, 2048):
+for variant in (0, 1):
+  lu.set_gemm_variant(variant)
+  for k in (128, 512, 1024, 2048):
     m = nn = n - k
     lu.gemm_sub(k, k, k, 0, 0, k, m, nn, k)          # warm-up
     torch.cuda.synchronize()
@@ -24,7 +26,8 @@ for k in (32, 128, 512, 2048):
         lu.gemm_sub(k, k, k, 0, 0, k, m, nn, k)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    out["k%d" % k] = {"ms": round(ms, 3), "tflops": round(2.0 * m * nn * k / ms * 1e-9, 2)}
+    out["v%d_k%d" % (variant, k)] = {"ms": round(ms, 3), "tflops": round(2.0 * m * nn * k / ms * 1e-9, 2)}
+lu.set_gemm_variant(0)
 # tall-skinny shapes of the panel recursion
 for (m, nn, k) in ((n - 64, 32, 32), (n - 128, 64, 64), (n - 256, 128, 128), (n - 512, 256, 256)):
     lu.gemm_sub(k, k, k, 0, 0, k, m, nn, k); torch.cuda.synchronize()

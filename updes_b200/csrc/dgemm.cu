@@ -22,8 +22,6 @@ namespace updes {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 16;
-constexpr int GEMM_CONSUMERS = 8;
-constexpr int GEMM_THREADS = GEMM_CONSUMERS * 32;
 
 struct GemmParams {
   double *C;           // base of the buffer holding C
@@ -83,23 +81,29 @@ __device__ __forceinline__ void tile_coords(long long t, int tiles_m, int tiles_
   nt = rem / gsz;
 }
 
-template <int BN>
+// NW = 8: one CTA per SM, 128 x BN tile (BN = 32 / 64 / 128).
+// NW = 4: "ping-pong" -- two independent 4-warp CTAs per SM, each with a 128 x 64 tile and the same
+//         64 x 32 per-warp accumulator block: while one CTA runs its epilogue (the exposed C
+//         read-modify-write) the other keeps the FP64 tensor pipe busy.
+template <int BN, int NW>
 struct GemmCfg {
+  static constexpr int THREADS = NW * 32;
+  static constexpr int MIN_CTAS = NW == 4 ? 2 : 1;
   static constexpr int WARPS_N = BN / 32;
-  static constexpr int WARPS_M = GEMM_CONSUMERS / WARPS_N;
+  static constexpr int WARPS_M = NW / WARPS_N;
   static constexpr int WM = GEMM_BM / WARPS_M;     // rows per warp
   static constexpr int MI = WM / 8;                // 8-row fragments per warp
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 8;
   static constexpr int B_BYTES = BN * GEMM_BK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 128 ? 6 : 8;
+  static constexpr int STAGES = NW == 4 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 4 ? 2 : 1))
 dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmParams P) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NW>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
@@ -108,7 +112,7 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; s++) {
       mbar_init(bars + 8 * s, 1);
-      mbar_init(bars + 8 * (Cfg::STAGES + s), GEMM_CONSUMERS);
+      mbar_init(bars + 8 * (Cfg::STAGES + s), NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,7 +126,7 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   // ------------------------------ producer state (thread 0) ------------------------------
   // No dedicated producer warp: a 9th warp would round the CTA up to 12 warps of register
   // allocation (168 regs/thread) and spill the 128 accumulator registers.  Thread 0 issues the TMA
-  // loads STAGES-1 k-tiles ahead of the consumers, all 8 warps (255 regs) do the math.
+  // loads STAGES-1 k-tiles ahead of the consumers, all warps (<= 255 regs) do the math.
   long long p_t = blockIdx.x;
   int p_kt = 0, p_stage = 0;
   uint32_t p_phase = 0;
@@ -290,20 +294,20 @@ int lu_bind_view(UpdesLU *h, int slot, const double *ptr, int64_t rows, int64_t 
   return 0;
 }
 
-template <int BN>
+template <int BN, int NW>
 static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const GemmParams &P, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NW>;
   static bool attr_set = false;
   if (!attr_set) {
-    UPDES_CUDA_TRY(cudaFuncSetAttribute(dgemm_sub_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(dgemm_sub_kernel<BN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const long long tiles = ((P.m + GEMM_BM - 1) / GEMM_BM) * ((P.n + BN - 1) / BN);
-  const int cap = (h->gemm_ctas > 0 && h->gemm_ctas < h->num_sms) ? h->gemm_ctas : h->num_sms;
+  const int cap = ((h->gemm_ctas > 0 && h->gemm_ctas < h->num_sms) ? h->gemm_ctas : h->num_sms) * Cfg::MIN_CTAS;
   const int grid = (int)(tiles < cap ? tiles : cap);
   prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
-  dgemm_sub_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, P);
+  dgemm_sub_kernel<BN, NW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, P);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
@@ -318,9 +322,12 @@ int dgemm_sub(UpdesLU *h, int va, int64_t ra, int64_t ca, int vb, int64_t rb, in
   if (!VA.ptr || !VB.ptr || !VC.ptr) return -2;
   GemmParams P;
   P.C = VC.ptr; P.ld = VC.ld; P.rc = rc; P.cc = cc; P.ra = ra; P.ca = ca; P.rb = rb; P.cb = cb; P.m = m; P.n = n; P.k = k;
-  if (n <= 32) return launch_gemm<32>(h, VA, VB, P, st);
-  if (n <= 64) return launch_gemm<64>(h, VA, VB, P, st);
-  return launch_gemm<128>(h, VA, VB, P, st);
+  if (n <= 32) return launch_gemm<32, 8>(h, VA, VB, P, st);
+  if (n <= 64) return launch_gemm<64, 8>(h, VA, VB, P, st);
+  // wide updates: ping-pong (two 128x64 CTAs per SM) once there are enough tiles to fill every slot
+  const long long tiles64 = ((m + GEMM_BM - 1) / GEMM_BM) * ((n + 63) / 64);
+  if (h->gemm_variant == 1 && tiles64 >= 2LL * h->num_sms) return launch_gemm<64, 4>(h, VA, VB, P, st);
+  return launch_gemm<128, 8>(h, VA, VB, P, st);
 }
 
 }  // namespace updes
@@ -347,5 +354,12 @@ extern "C" int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas) {
   if (!handle) return -1;
   if (ctas < 0) return -2;
   handle->gemm_ctas = ctas;
+  return 0;
+}
+
+extern "C" int updes_lu_set_gemm_variant(UpdesLU *handle, int variant) {
+  if (!handle) return -1;
+  if (variant < 0 || variant > 1) return -2;
+  handle->gemm_variant = variant;
   return 0;
 }

@@ -20,6 +20,7 @@ struct UpdesLU {
   int64_t n = 0, ld = 0;   // rows and leading dimension of slot 0
   int num_sms = 148;
   int gemm_ctas = 0;       // 0 = one CTA per SM; smaller leaves SMs free for concurrent NCCL kernels
+  int gemm_variant = 0;    // 0: one 128x128 CTA per SM; 1: ping-pong, two 128x64 CTAs per SM
   MatView view[UPDES_MAX_VIEWS];
   // device workspace of the panel kernel
   double *cand = nullptr;          // [2][num_sms][PANEL_W] candidate pivot rows

@@ -51,6 +51,9 @@ class LUFactorization:
         _lib.check(rc, "updes_lu_solve")
         return B
 
+    def set_gemm_variant(self, variant: int):
+        _lib.check(self._lib.updes_lu_set_gemm_variant(self._handle, variant), "updes_lu_set_gemm_variant")
+
     def gemm_sub(self, rc_, cc, ra, ca, rb, cb, m, n, k):
         """C -= A @ B on sub-blocks of the bound matrix (exposed for kernel-level tests)."""
         rc = self._lib.updes_dgemm_sub(self._handle, self.K.data_ptr(), rc_, cc, ra, ca, rb, cb, m, n, k,
