@@ -135,6 +135,9 @@ int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t 
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule: 0 = one 128x128 CTA per SM, 1 = ping-pong (two 128x64 CTAs per SM) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
+/* test hook: rows the 32-wide register-resident panel holds (0 = default 148*640); smaller values
+ * force the 16- / 8-wide base panels used for panels taller than 94 720 / 189 440 rows */
+int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows);
 /* LU of the tall panel rows [r0, rows) x columns [c0, c0+nc) of `slot`; interchanges are applied to
  * the panel columns only; ipiv[r0 .. r0+nc) receives the pivots. */
 int updes_lu_panel_factor(UpdesLU *handle, int slot, int64_t r0, int64_t c0, int64_t nc, int32_t *ipiv,

@@ -74,6 +74,24 @@ def test_lu_factor_reconstructs(n):
     assert np.array_equal(piv, piv_ref.numpy() - 1)
 
 
+@pytest.mark.parametrize("cap", [600, 300])
+def test_lu_tall_panel_paths(cap):
+    """Panels taller than the 32-wide register-resident kernel fall back to 16- and 8-wide base panels
+    (250k-row panels of the multi-GPU path); force that with a small capacity and compare with LAPACK."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    n = 1000                                          # cap=600 -> 16-wide at the top; cap=300 -> 8-wide, then 16, then 32
+    A, K = _matrix(n, seed=77)
+    lu = LUFactorization(K, n)
+    lu.set_panel_capacity(cap)
+    lu.factor()
+    torch.cuda.synchronize()
+    assert lu.zero_pivot() == 0
+    lu_ref, piv_ref = torch.linalg.lu_factor(A)
+    assert np.array_equal(lu.ipiv.cpu().numpy(), piv_ref.numpy() - 1)
+    assert (K[:, :n].cpu() - lu_ref).abs().max().item() <= 1e-10 * lu_ref.abs().max().item()
+
+
 @pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 1), (2051, 5)])
 def test_lu_solve(n, nrhs):
     import torch

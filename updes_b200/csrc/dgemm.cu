@@ -363,3 +363,12 @@ extern "C" int updes_lu_set_gemm_variant(UpdesLU *handle, int variant) {
   handle->gemm_variant = variant;
   return 0;
 }
+
+/* test hook: pretend the 32-wide panel kernel holds only `rows` rows, to exercise the 16- and 8-wide
+ * base panels that very tall (multi-GPU, > 94 720-row) panels use */
+extern "C" int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows) {
+  if (!handle) return -1;
+  if (rows < 0) return -2;
+  handle->panel_cap = rows;
+  return 0;
+}

@@ -20,6 +20,7 @@ struct UpdesLU {
   int64_t n = 0, ld = 0;   // rows and leading dimension of slot 0
   int num_sms = 148;
   int gemm_ctas = 0;       // 0 = one CTA per SM; smaller leaves SMs free for concurrent NCCL kernels
+  int64_t panel_cap = 0;   // rows a 32-wide register-resident panel can hold (0 = num_sms * 640); test hook
   int gemm_variant = 0;    // 0: one 128x128 CTA per SM; 1: ping-pong, two 128x64 CTAs per SM
   MatView view[UPDES_MAX_VIEWS];
   // device workspace of the panel kernel
@@ -54,5 +55,7 @@ int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int 
 int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t swap_lo, int64_t swap_hi,
                  int32_t *ipiv, int32_t *info, cudaStream_t st);
 int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st);
+int rank8_update(UpdesLU *h, int v, int64_t ra, int64_t ca, int64_t rb, int64_t cb, int64_t rc, int64_t cc, int64_t m,
+                 int nc, cudaStream_t st);
 
 }  // namespace updes

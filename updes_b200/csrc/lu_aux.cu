@@ -87,10 +87,11 @@ static int trsm_base(UpdesLU *h, int vl, int64_t rl, int64_t cl, int nb, int vb,
                      int64_t ncols, cudaStream_t st) {
   const MatView &VL = h->view[vl], &VB = h->view[vb];
   const unsigned grid = (unsigned)((ncols + 127) / 128);
-  if (nb != 32 && nb != 16) return -4;
+  if (nb != 32 && nb != 16 && nb != 8) return -4;
   prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
   if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
-  else trsm_base_kernel<16><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  else if (nb == 16) trsm_base_kernel<16><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  else trsm_base_kernel<8><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
@@ -110,6 +111,46 @@ int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int 
   rc = dgemm_sub(h, vl, rl + hlf, cl, vb, rb, cb, vb, rb + hlf, cb, n1 - hlf, ncols, hlf, st);
   if (rc) return rc;
   return trsm_unit_lower(h, vl, rl + hlf, cl + hlf, n1 - hlf, vb, rb + hlf, cb, ncols, st);
+}
+
+// ---- rank-8 update of a narrow block ------------------------------------------------------------------
+// C[m x nc] -= A[m x 8] * B[8 x nc], nc <= 8.  Only used inside panels taller than 189 440 rows, whose
+// base width drops to 8 columns (the DMMA GEMM needs k >= 16).  One thread per row.
+__global__ void __launch_bounds__(256) rank8_update_kernel(double *K, long long ld, long long ra, long long ca,
+                                                           long long rb, long long cb, long long rc, long long cc,
+                                                           long long m, int nc) {
+  __shared__ double B[8][8];
+  if (threadIdx.x < 64) {
+    const int i = threadIdx.x >> 3, j = threadIdx.x & 7;
+    B[i][j] = j < nc ? K[(rb + i) * ld + cb + j] : 0.0;
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double *arow = K + (ra + i) * ld + ca;
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = arow[k];
+  double *crow = K + (rc + i) * ld + cc;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (j < nc) {
+      double v = crow[j];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v = fma(-a[k], B[k][j], v);
+      crow[j] = v;
+    }
+  }
+}
+
+int rank8_update(UpdesLU *h, int v, int64_t ra, int64_t ca, int64_t rb, int64_t cb, int64_t rc, int64_t cc, int64_t m,
+                 int nc, cudaStream_t st) {
+  if (m <= 0 || nc <= 0) return 0;
+  if (nc > 8) return -10;
+  rank8_update_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(h->view[v].ptr, h->view[v].ld, ra, ca, rb, cb, rc, cc,
+                                                                 m, nc);
+  UPDES_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---- pivots -> permutation ------------------------------------------------------------------------

@@ -22,7 +22,7 @@ int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t 
   if (nc <= 0) return 0;
   const int64_t rows = h->view[v].rows;
   const int W = panel_width_for(h, rows - r0);
-  if (W < 16) return -2;   // panel taller than the register-resident kernel supports
+  if (W < 8) return -2;    // panel taller than the register-resident kernel supports (> 378 880 rows)
   if (nc <= W) {
     int rc = lu_panel_base(h, v, r0, c0, (int)nc, ipiv, info, st);
     if (rc) return rc;
@@ -31,14 +31,16 @@ int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t 
     return swap_rows(h, v, c0 + nc, swap_hi - (c0 + nc), r0, nc, ipiv, st);
   }
   int64_t n1;
-  if (nc <= 32) n1 = 16;
+  if (nc <= 16) n1 = 8;           // only reached when W == 8 (very tall panels)
+  else if (nc <= 32) n1 = 16;
   else n1 = (nc / 2 + 31) / 32 * 32;
   int rc = lu_recursive(h, v, r0, c0, n1, swap_lo, swap_hi, ipiv, info, st);
   if (rc) return rc;
   const int64_t n2 = nc - n1;
   rc = trsm_unit_lower(h, v, r0, c0, n1, v, r0, c0 + n1, n2, st);
   if (rc) return rc;
-  rc = dgemm_sub(h, v, r0 + n1, c0, v, r0, c0 + n1, v, r0 + n1, c0 + n1, rows - (r0 + n1), n2, n1, st);
+  if (n1 == 8) rc = rank8_update(h, v, r0 + n1, c0, r0, c0 + n1, r0 + n1, c0 + n1, rows - (r0 + n1), (int)n2, st);
+  else rc = dgemm_sub(h, v, r0 + n1, c0, v, r0, c0 + n1, v, r0 + n1, c0 + n1, rows - (r0 + n1), n2, n1, st);
   if (rc) return rc;
   return lu_recursive(h, v, r0 + n1, c0 + n1, n2, swap_lo, swap_hi, ipiv, info, st);
 }

@@ -231,7 +231,7 @@ static int launch_panel(UpdesLU *h, PanelParams &P, int threads, cudaStream_t st
 
 // widest base panel the register-resident kernel can take for a panel of m rows
 int panel_width_for(const UpdesLU *h, int64_t m) {
-  const int64_t cap = (int64_t)h->num_sms * PANEL_THREADS;
+  const int64_t cap = h->panel_cap > 0 ? h->panel_cap : (int64_t)h->num_sms * PANEL_THREADS;
   if (m <= cap) return 32;
   if (m <= 2 * cap) return 16;
   if (m <= 4 * cap) return 8;

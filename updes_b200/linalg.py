@@ -51,6 +51,9 @@ class LUFactorization:
         _lib.check(rc, "updes_lu_solve")
         return B
 
+    def set_panel_capacity(self, rows: int):
+        _lib.check(self._lib.updes_lu_set_panel_capacity(self._handle, rows), "updes_lu_set_panel_capacity")
+
     def set_gemm_variant(self, variant: int):
         _lib.check(self._lib.updes_lu_set_gemm_variant(self._handle, variant), "updes_lu_set_gemm_variant")
 
