@@ -47,6 +47,12 @@ def lu_flops(n):
     return 2.0 / 3.0 * float(n) ** 3
 
 
+def default_side(gpus):
+    """SquareCloud side per GPU count: constant HBM footprint per GPU (side = 300 N^(1/4)), with the
+    BASELINE.json configurations at the ends: 300x300 on 1 GPU, 500x500 on 8."""
+    return {1: 300, 2: 357, 4: 424, 8: 500}.get(gpus, int(round(300 * gpus ** 0.25)))
+
+
 def workload_name(nx):
     return "Synthetic Laplace SquareCloud %dx%d (%d nodes), polyharmonic a=1, max_degree=1, FP64" % (nx, nx, nx * nx)
 
@@ -103,7 +109,7 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args.nx or int(round(300 * args.gpus ** 0.25))), "sample": "SquareCloud %dx%d" % (nx, nx)},
+            "config": {"workload": workload_name(args.nx or default_side(args.gpus)), "sample": "SquareCloud %dx%d" % (nx, nx)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -160,9 +166,12 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL only moves one panel per block step; keep its kernels small so they do not take SMs
+        # from the update GEMM they overlap with (the GEMM's dynamic tile scheduler absorbs the rest)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    nx = args.nx if args.nx else int(round(300 * world ** 0.25))
+    nx = args.nx if args.nx else default_side(world)
     if world > 1:
         return run_gpu_arm_distributed(args, world, rank, local, nx)
     cloud = u.SquareCloud(Nx=nx, Ny=nx, facet_types=FACETS)

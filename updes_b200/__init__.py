@@ -12,7 +12,7 @@ from .operators import (BatchPoints, OperatorLoweringError, SteadySol, boundary_
                         compute_coefficients, core_compute_coefficients, divergence, divergence_vec, dot,
                         duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vec, laplacian,
                         laplacian_vec, lower_diff_operator, nodal_div_grad, nodal_gradient, nodal_laplacian,
-                        nodal_value, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
+                        nodal_value, pde_multi_solver, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
                         zerofy_periodic_cond)
 
 __version__ = "0.1.0"

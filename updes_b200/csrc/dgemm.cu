@@ -6,6 +6,7 @@
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), measured 37.0 TFLOP/s raw on B200 (profiles/r01_ceilings.json).
 //
 // Structure (one persistent CTA per SM, static tile schedule):
+//   * tiles are handed out dynamically (atomic counter), so CTAs delayed by co-running kernels take less;
 //   * thread 0 doubles as the producer: it issues TMA (cp.async.bulk.tensor) loads of the
 //     A tile (128 rows x 16 k) and the B tile (16 k x BN cols) STAGES-1 k-tiles ahead into a
 //     shared-memory ring guarded by full/empty mbarriers;
@@ -30,6 +31,8 @@ struct GemmParams {
   long long ra, ca;    // A block origin (m x k)
   long long rb, cb;    // B block origin (k x n)
   long long m, n, k;
+  unsigned int *counter;       // dynamic tile scheduler: next tile index of THIS launch (starts at 0)
+  unsigned int *next_counter;  // counter of the next launch on the stream, reset by this one
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,17 +130,38 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   // No dedicated producer warp: a 9th warp would round the CTA up to 12 warps of register
   // allocation (168 regs/thread) and spill the 128 accumulator registers.  Thread 0 issues the TMA
   // loads STAGES-1 k-tiles ahead of the consumers, all warps (<= 255 regs) do the math.
-  long long p_t = blockIdx.x;
+  //
+  // Tiles are handed out dynamically (one atomicAdd per tile on a per-launch counter) rather than
+  // round-robin: when other kernels hold some SMs for a while -- NCCL's broadcast on the multi-GPU
+  // path -- the CTAs that start late simply take fewer tiles instead of stretching the tail.
+  const uint32_t stage_tile = bars + 16 * Cfg::STAGES;   // int[STAGES]: tile id the stage belongs to (-1 = no more work)
+  long long p_t = -1, p_next = -1;
   int p_kt = 0, p_stage = 0;
   uint32_t p_phase = 0;
+  bool p_done = false;
+  auto fetch_tile = [&]() -> long long {
+    const unsigned int t = atomicAdd(P.counter, 1u);
+    return (long long)t < ntiles ? (long long)t : -1;
+  };
   auto produce_one = [&]() {
-    if (p_t >= ntiles) return;
+    if (p_done) return;
+    if (p_kt == 0) {
+      p_t = p_next;
+      if (p_t >= 0) p_next = fetch_tile();     // requested a whole tile ahead of its first use
+    }
+    mbar_wait(bars + 8 * (Cfg::STAGES + p_stage), p_phase ^ 1);
+    const uint32_t full = bars + 8 * p_stage;
+    if (p_t < 0) {                               // sentinel stage: tells the consumers to stop
+      asm volatile("st.shared.s32 [%0], %1;" ::"r"(stage_tile + 4 * p_stage), "r"(-1) : "memory");
+      mbar_arrive(full);
+      p_done = true;
+      return;
+    }
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(stage_tile + 4 * p_stage), "r"((int)p_t) : "memory");
     int mt, nt;
     tile_coords(p_t, tiles_m, tiles_n, mt, nt);
     const int arow = (int)(P.ra + (long long)mt * GEMM_BM);
     const int bcol = (int)(P.cb + (long long)nt * BN);
-    mbar_wait(bars + 8 * (Cfg::STAGES + p_stage), p_phase ^ 1);
-    const uint32_t full = bars + 8 * p_stage;
     mbar_expect_tx(full, Cfg::STAGE_BYTES);
     const uint32_t sa = smem_base + p_stage * Cfg::STAGE_BYTES;
     tma_load_2d(sa, &mapA, (int)(P.ca + p_kt * GEMM_BK), arow, full);
@@ -145,9 +169,11 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int g = 0; g < BN / 16; g++)
       tma_load_2d(sa + Cfg::A_BYTES + g * 2048, &mapB, bcol + 16 * g, (int)(P.rb + p_kt * GEMM_BK), full);
     if (++p_stage == Cfg::STAGES) { p_stage = 0; p_phase ^= 1; }
-    if (++p_kt == ktiles) { p_kt = 0; p_t += gridDim.x; }
+    if (++p_kt == ktiles) p_kt = 0;
   };
   if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) *P.next_counter = 0u;
+    p_next = fetch_tile();
 #pragma unroll 1
     for (int i = 0; i < Cfg::STAGES - 1; i++) produce_one();
   }
@@ -174,7 +200,12 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   int stage = 0;
   uint32_t phase = 0;
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  while (true) {
+    if (threadIdx.x == 0) produce_one();
+    mbar_wait(bars + 8 * stage, phase);
+    int t;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(stage_tile + 4 * stage) : "memory");
+    if (t < 0) break;
     int mt, nt;
     tile_coords(t, tiles_m, tiles_n, mt, nt);
     double acc[Cfg::MI][4][2];
@@ -184,8 +215,10 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int jn = 0; jn < 4; jn++) { acc[i][jn][0] = 0.0; acc[i][jn][1] = 0.0; }
 
     for (int kt = 0; kt < ktiles; kt++) {
-      if (threadIdx.x == 0) produce_one();
-      mbar_wait(bars + 8 * stage, phase);
+      if (kt > 0) {
+        if (threadIdx.x == 0) produce_one();
+        mbar_wait(bars + 8 * stage, phase);
+      }
       const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES + a_row_off;
       const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
 #pragma unroll
@@ -306,8 +339,12 @@ static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const G
   const long long tiles = ((P.m + GEMM_BM - 1) / GEMM_BM) * ((P.n + BN - 1) / BN);
   const int cap = ((h->gemm_ctas > 0 && h->gemm_ctas < h->num_sms) ? h->gemm_ctas : h->num_sms) * Cfg::MIN_CTAS;
   const int grid = (int)(tiles < cap ? tiles : cap);
+  GemmParams Q = P;
+  Q.counter = h->gemm_counters + (h->gemm_launch_id % UPDES_GEMM_COUNTERS);
+  Q.next_counter = h->gemm_counters + ((h->gemm_launch_id + 1) % UPDES_GEMM_COUNTERS);
+  h->gemm_launch_id++;
   prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
-  dgemm_sub_kernel<BN, NW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, P);
+  dgemm_sub_kernel<BN, NW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, Q);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;

@@ -15,6 +15,7 @@ struct MatView {
 };
 
 constexpr int UPDES_MAX_VIEWS = 4;
+constexpr int UPDES_GEMM_COUNTERS = 1024;
 
 struct UpdesLU {
   int64_t n = 0, ld = 0;   // rows and leading dimension of slot 0
@@ -30,6 +31,8 @@ struct UpdesLU {
   int32_t *candrow = nullptr;      // [2][num_sms]
   unsigned int *barrier = nullptr; // grid barrier counter (monotonic)
   unsigned int barrier_count = 0;  // host mirror of the counter after all enqueued panels
+  unsigned int *gemm_counters = nullptr;   // ring of per-launch tile counters (dynamic scheduler)
+  unsigned long long gemm_launch_id = 0;
   int32_t *perm = nullptr;         // [n] row permutation of the last factorisation (for solves)
   double *xbuf = nullptr;          // solve scratch
 };

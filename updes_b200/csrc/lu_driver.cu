@@ -63,8 +63,10 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   if (e == cudaSuccess) e = cudaMalloc(&h->candrow, sizeof(int32_t) * 2 * h->num_sms);
   if (e == cudaSuccess) e = cudaMalloc(&h->barrier, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->barrier, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->gemm_counters, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
+  if (e == cudaSuccess) e = cudaMemset(h->gemm_counters, 0, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
   if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * n * 8);   // X and Y, 4 right-hand sides each
   if (e != cudaSuccess) {
     updes_lu_destroy(h);
     return (int)e;
@@ -76,7 +78,7 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
 extern "C" int updes_lu_destroy(UpdesLU *h) {
   if (!h) return 0;
   cudaFree(h->cand); cudaFree(h->top); cudaFree(h->candval); cudaFree(h->candrow);
-  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf);
+  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters);
   delete h;
   return 0;
 }

@@ -27,100 +27,154 @@ __global__ void copy_back_kernel(double *B, long long ldb, int nrhs, long long n
   for (int f = 0; f < nrhs; f++) B[f * ldb + i] = X[f * n + i];
 }
 
-// Solve the diagonal block [k0, k0+nb) in place.  UPPER = false: unit lower (forward);
-// UPPER = true: non-unit upper (backward).
+// One block step of the substitution, fused in one launch.  Every CTA
+//   A. stages the nb x nb diagonal block T = LU[k0.., c0..] in shared memory (the block is read from
+//      L2 by all CTAs; 128 KB each) and the current right-hand-side block,
+//   B. solves it redundantly: four 32 x 32 triangular solves by one warp (the 32 unknowns live in the
+//      lanes, one shuffle broadcast per column) interleaved with block updates by all threads --
+//      plain substitution, so the solve keeps LAPACK's backward stability (no explicit inverses),
+//   C. subtracts the block's contribution from its share of the remaining rows, one warp per row
+//      (a 1 KB contiguous row segment dotted with the block solution held in shared memory).
+// CTA 0 stores the solved block into `Yout`; the remaining rows are updated in place in `X`.
+// UPPER = false: unit lower (forward sweep); UPPER = true: upper with diagonal (backward sweep).
+constexpr int STEP_THREADS = 1024;
+constexpr size_t STEP_SMEM = sizeof(double) * (SB * (SB + 1) + SOLVE_MAX_RHS * SB);
+
 template <bool UPPER>
-__global__ void __launch_bounds__(SB) diag_solve_kernel(const double *LU, long long ld, long long n, long long k0,
-                                                        long long c0, int nb, double *X, int nrhs) {
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+tri_step_kernel(const double *LU, long long ld, long long n, long long k0, long long c0, int nb, long long i0,
+                long long i1, double *X, double *Yout, int nrhs) {
   extern __shared__ double sm[];
   double *T = sm;                       // [SB][SB+1]
   double *xs = sm + SB * (SB + 1);      // [nrhs][SB]
-  const int tid = threadIdx.x;
-  for (int i = 0; i < nb; i++)
-    if (tid < nb) T[i * (SB + 1) + tid] = LU[(k0 + i) * ld + c0 + tid];
-  for (int f = 0; f < nrhs; f++)
-    if (tid < nb) xs[f * SB + tid] = X[f * n + k0 + tid];
-  __syncthreads();
-  if (!UPPER) {
-    for (int c = 0; c < nb; c++) {
-      if (tid > c && tid < nb) {
-        const double l = T[tid * (SB + 1) + c];
-        for (int f = 0; f < nrhs; f++) xs[f * SB + tid] = fma(-l, xs[f * SB + c], xs[f * SB + tid]);
-      }
-      __syncthreads();
-    }
-  } else {
-    for (int c = nb - 1; c >= 0; c--) {
-      if (tid == c)
-        for (int f = 0; f < nrhs; f++) xs[f * SB + c] = xs[f * SB + c] / T[c * (SB + 1) + c];
-      __syncthreads();
-      if (tid < c) {
-        const double u = T[tid * (SB + 1) + c];
-        for (int f = 0; f < nrhs; f++) xs[f * SB + tid] = fma(-u, xs[f * SB + c], xs[f * SB + tid]);
-      }
-      __syncthreads();
-    }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = STEP_THREADS / 32;
+  // ---- A. stage T and the rhs block ------------------------------------------------------------
+  for (int r = warp; r < nb; r += NWARPS) {
+    const double *src = LU + (k0 + r) * ld + c0;
+    for (int c = lane; c < nb; c += 32) T[r * (SB + 1) + c] = src[c];
   }
-  for (int f = 0; f < nrhs; f++)
-    if (tid < nb) X[f * n + k0 + tid] = xs[f * SB + tid];
-}
-
-// X[i] -= sum_c LU[i][k0 + c] * X[k0 + c] for rows i in [i0, i1); one warp per row.
-__global__ void __launch_bounds__(256) block_update_kernel(const double *LU, long long ld, long long n, long long k0,
-                                                          long long c0, int nb, long long i0, long long i1, double *X,
-                                                          int nrhs) {
-  __shared__ double xs[SOLVE_MAX_RHS][SB];
-  for (int t = threadIdx.x; t < nrhs * SB; t += blockDim.x) {
+  for (int t = tid; t < nrhs * SB; t += STEP_THREADS) {
     const int f = t / SB, c = t % SB;
-    xs[f][c] = c < nb ? X[f * n + k0 + c] : 0.0;
+    xs[f * SB + c] = c < nb ? X[f * n + k0 + c] : 0.0;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long i = i0 + (long long)blockIdx.x * 8 + warp;
-  if (i >= i1) return;
-  const double *row = LU + i * ld + c0;
-  double acc[SOLVE_MAX_RHS] = {0, 0, 0, 0};
-  if (nb == SB) {
-    // 128 contiguous doubles: each lane takes two 16-byte pieces (c0 and ld are even)
-    const double2 v0 = *reinterpret_cast<const double2 *>(row + 2 * lane);
-    const double2 v1 = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
-    for (int f = 0; f < nrhs; f++) {
-      acc[f] = v0.x * xs[f][2 * lane];
-      acc[f] = fma(v0.y, xs[f][2 * lane + 1], acc[f]);
-      acc[f] = fma(v1.x, xs[f][64 + 2 * lane], acc[f]);
-      acc[f] = fma(v1.y, xs[f][64 + 2 * lane + 1], acc[f]);
+  // ---- B. triangular solve of the block ------------------------------------------------------------
+  const int nsub = (nb + 31) / 32;
+  for (int q = 0; q < nsub; q++) {
+    const int sb = UPPER ? (nsub - 1 - q) : q;
+    const int base = sb * 32;
+    const int cnt = min(32, nb - base);
+    if (warp == 0) {
+      for (int f = 0; f < nrhs; f++) {
+        double x = lane < cnt ? xs[f * SB + base + lane] : 0.0;
+        if (!UPPER) {
+          for (int c = 0; c < cnt; c++) {
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane > c && lane < cnt) x = fma(-T[(base + lane) * (SB + 1) + base + c], xc, x);
+          }
+        } else {
+          for (int c = cnt - 1; c >= 0; c--) {
+            if (lane == c) x = x / T[(base + c) * (SB + 1) + base + c];
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane < c) x = fma(-T[(base + lane) * (SB + 1) + base + c], xc, x);
+          }
+        }
+        if (lane < cnt) xs[f * SB + base + lane] = x;
+      }
     }
-  } else {
-    for (int c = lane; c < nb; c += 32) {
-      const double v = row[c];
-      for (int f = 0; f < nrhs; f++) acc[f] = fma(v, xs[f][c], acc[f]);
+    __syncthreads();
+    // rows of the block still to be solved lose the contribution of sub-block sb
+    const int rbeg = UPPER ? 0 : base + 32, rend = UPPER ? base : nb;
+    for (int t = tid; t < (rend - rbeg) * nrhs; t += STEP_THREADS) {
+      const int f = t / (rend - rbeg), r = rbeg + t % (rend - rbeg);
+      double v = xs[f * SB + r];
+      const double *trow = T + r * (SB + 1) + base;
+      for (int c = 0; c < cnt; c++) v = fma(-trow[c], xs[f * SB + base + c], v);
+      xs[f * SB + r] = v;
     }
+    __syncthreads();
   }
-  for (int f = 0; f < nrhs; f++) {
-    double a = acc[f];
+  if (blockIdx.x == 0)
+    for (int t = tid; t < nrhs * nb; t += STEP_THREADS) {
+      const int f = t / nb, c = t % nb;
+      Yout[f * n + k0 + c] = xs[f * SB + c];
+    }
+  // ---- C. update the remaining rows -------------------------------------------------------------------
+  // four rows in flight per warp (4 KB of loads outstanding) and fire-and-forget reductions into X:
+  // the phase is latency-bound otherwise (one 1 KB row per warp and a dependent read-modify-write).
+  constexpr int RU = 4;
+  const long long wstride = (long long)gridDim.x * NWARPS;
+  for (long long i = i0 + (long long)blockIdx.x * NWARPS + warp; i < i1; i += RU * wstride) {
+    if (nb == SB) {
+      double2 v0[RU], v1[RU];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if (lane == 0) X[f * n + i] -= a;
+      for (int u = 0; u < RU; u++) {
+        const long long r = i + u * wstride;
+        if (r < i1) {
+          const double *row = LU + r * ld + c0;
+          v0[u] = *reinterpret_cast<const double2 *>(row + 2 * lane);
+          v1[u] = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
+        } else {
+          v0[u] = make_double2(0.0, 0.0); v1[u] = v0[u];
+        }
+      }
+      for (int f = 0; f < nrhs; f++) {
+        const double *xf = xs + f * SB;
+        const double x0 = xf[2 * lane], x1 = xf[2 * lane + 1], x2 = xf[64 + 2 * lane], x3 = xf[64 + 2 * lane + 1];
+        double a[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) a[u] = fma(v1[u].y, x3, fma(v1[u].x, x2, fma(v0[u].y, x1, v0[u].x * x0)));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int u = 0; u < RU; u++) a[u] += __shfl_xor_sync(0xffffffffu, a[u], off);
+        if (lane < RU) {
+          const long long r = i + lane * wstride;
+          double mine = a[0];
+#pragma unroll
+          for (int u = 1; u < RU; u++) mine = lane == u ? a[u] : mine;
+          if (r < i1) atomicAdd(X + f * n + r, -mine);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < RU; u++) {
+        const long long r = i + u * wstride;
+        if (r >= i1) break;
+        const double *row = LU + r * ld + c0;
+        for (int f = 0; f < nrhs; f++) {
+          double a = 0.0;
+          for (int c = lane; c < nb; c += 32) a = fma(row[c], xs[f * SB + c], a);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+          if (lane == 0) atomicAdd(X + f * n + r, -a);
+        }
+      }
+    }
   }
 }
-
-constexpr size_t DIAG_SMEM = sizeof(double) * (SB * (SB + 1) + SOLVE_MAX_RHS * SB);
 
 static int ensure_solve_attrs() {
   static bool attr = false;
   if (!attr) {
-    UPDES_CUDA_TRY(cudaFuncSetAttribute(diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    UPDES_CUDA_TRY(cudaFuncSetAttribute(diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM));
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM));
     attr = true;
   }
   return 0;
 }
 
-// One column block [c0, c0+w) of a (possibly column-distributed) factor whose diagonal sits at
-// rows [r0, r0+w): forward (unit lower) or backward (upper) substitution restricted to this block,
-// updating X for all rows below / above.  X holds the full-length right-hand sides, [nrhs][n].
-int tri_block_sweep(const double *LU, long long ld, long long n, bool upper, long long r0, long long c0, long long w,
-                    double *X, int nrhs, cudaStream_t st) {
+static int step_grid(int num_sms, long long rows) {
+  const long long want = (rows + 127) / 128;        // 32 warps x 4 rows per CTA pass
+  return (int)(want < 1 ? 1 : (want > num_sms ? num_sms : want));
+}
+
+// Substitution restricted to one column block [c0, c0+w) whose diagonal sits at rows [r0, r0+w).
+// Forward (unit lower): rows below r0 of X are the running right-hand side; the solved block goes to Y.
+// Backward (upper): same upwards.  X and Y are full-length [nrhs][n] vectors (X != Y).
+int tri_block_sweep(int num_sms, const double *LU, long long ld, long long n, bool upper, long long r0, long long c0,
+                    long long w, double *X, double *Y, int nrhs, cudaStream_t st) {
   int rc = ensure_solve_attrs();
   if (rc) return rc;
   const long long nsub = (w + SB - 1) / SB;
@@ -129,55 +183,24 @@ int tri_block_sweep(const double *LU, long long ld, long long n, bool upper, lon
     const long long k0 = r0 + s * SB, cc = c0 + s * SB;
     const int nb = (int)((w - s * SB) < SB ? (w - s * SB) : SB);
     if (!upper) {
-      diag_solve_kernel<false><<<1, SB, DIAG_SMEM, st>>>(LU, ld, n, k0, cc, nb, X, nrhs);
-      UPDES_LAUNCH_CHECK();
       const long long i0 = k0 + nb;
-      if (i0 < n) {
-        block_update_kernel<<<(unsigned)((n - i0 + 7) / 8), 256, 0, st>>>(LU, ld, n, k0, cc, nb, i0, n, X, nrhs);
-        UPDES_LAUNCH_CHECK();
-      }
+      tri_step_kernel<false><<<step_grid(num_sms, n - i0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, i0, n, X,
+                                                                                         Y, nrhs);
     } else {
-      diag_solve_kernel<true><<<1, SB, DIAG_SMEM, st>>>(LU, ld, n, k0, cc, nb, X, nrhs);
-      UPDES_LAUNCH_CHECK();
-      if (k0 > 0) {
-        block_update_kernel<<<(unsigned)((k0 + 7) / 8), 256, 0, st>>>(LU, ld, n, k0, cc, nb, 0, k0, X, nrhs);
-        UPDES_LAUNCH_CHECK();
-      }
+      tri_step_kernel<true><<<step_grid(num_sms, k0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, 0, k0, X, Y,
+                                                                                     nrhs);
     }
+    UPDES_LAUNCH_CHECK();
   }
   return 0;
 }
 
-static int solve_chunk(UpdesLU *h, const double *LU, double *X, int nrhs, cudaStream_t st) {
-  const long long n = h->n, ld = h->ld;
-  const size_t smem = DIAG_SMEM;
-  int rc0 = ensure_solve_attrs();
-  if (rc0) return rc0;
-  const long long nblk = (n + SB - 1) / SB;
-  // forward: L y = P b
-  for (long long kb = 0; kb < nblk; kb++) {
-    const long long k0 = kb * SB;
-    const int nb = (int)((n - k0) < SB ? (n - k0) : SB);
-    diag_solve_kernel<false><<<1, SB, smem, st>>>(LU, ld, n, k0, k0, nb, X, nrhs);
-    UPDES_LAUNCH_CHECK();
-    const long long i0 = k0 + nb;
-    if (i0 < n) {
-      block_update_kernel<<<(unsigned)((n - i0 + 7) / 8), 256, 0, st>>>(LU, ld, n, k0, k0, nb, i0, n, X, nrhs);
-      UPDES_LAUNCH_CHECK();
-    }
-  }
-  // backward: U x = y
-  for (long long kb = nblk - 1; kb >= 0; kb--) {
-    const long long k0 = kb * SB;
-    const int nb = (int)((n - k0) < SB ? (n - k0) : SB);
-    diag_solve_kernel<true><<<1, SB, smem, st>>>(LU, ld, n, k0, k0, nb, X, nrhs);
-    UPDES_LAUNCH_CHECK();
-    if (k0 > 0) {
-      block_update_kernel<<<(unsigned)((k0 + 7) / 8), 256, 0, st>>>(LU, ld, n, k0, k0, nb, 0, k0, X, nrhs);
-      UPDES_LAUNCH_CHECK();
-    }
-  }
-  return 0;
+// whole solve on one GPU: X = P b in xbuf[0]; forward sweep X -> Y; backward sweep Y -> X
+static int solve_chunk(UpdesLU *h, const double *LU, double *X, double *Y, int nrhs, cudaStream_t st) {
+  const long long n = h->n;
+  int rc = tri_block_sweep(h->num_sms, LU, h->ld, n, false, 0, 0, n, X, Y, nrhs, st);
+  if (rc) return rc;
+  return tri_block_sweep(h->num_sms, LU, h->ld, n, true, 0, 0, n, Y, X, nrhs, st);
 }
 
 }  // namespace updes
@@ -200,7 +223,7 @@ extern "C" int updes_lu_solve(UpdesLU *h, const double *LU, const int32_t *ipiv,
     gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf);
     UPDES_LAUNCH_CHECK();
     prof_begin(PROF_SOLVE, 8.0 * (double)n * (double)n, st);
-    int rc = solve_chunk(h, LU, h->xbuf, nf, st);
+    int rc = solve_chunk(h, LU, h->xbuf, h->xbuf + (size_t)SOLVE_MAX_RHS * n, nf, st);
     prof_end(st);
     if (rc) return rc;
     copy_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, n, h->xbuf);
@@ -228,6 +251,13 @@ extern "C" int updes_lu_permute_rhs(UpdesLU *h, const double *B, int64_t ldb, in
   return 0;
 }
 
+__global__ void copy_block_kernel(double *X, const double *Y, long long n, long long r0, long long w, int nrhs) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= w * nrhs) return;
+  const long long f = t / w, c = t % w;
+  X[f * n + r0 + c] = Y[f * n + r0 + c];
+}
+
 extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0, int64_t c0, int64_t width,
                                      double *X, int nrhs, void *stream) {
   using namespace updes;
@@ -237,6 +267,12 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
   if (c0 < 0 || (c0 & 1) || c0 + width > h->view[slot].ld) return -5;
   if (!X) return -7;
   if (nrhs <= 0 || nrhs > SOLVE_MAX_RHS) return -8;
-  return tri_block_sweep(h->view[slot].ptr, h->view[slot].ld, h->view[slot].rows, upper != 0, r0, c0, width, X, nrhs,
-                         (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = h->view[slot].rows;
+  double *Y = h->xbuf + (size_t)SOLVE_MAX_RHS * h->n;     // scratch for the solved block
+  int rc = tri_block_sweep(h->num_sms, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, r0, c0, width, X, Y, nrhs, st);
+  if (rc) return rc;
+  copy_block_kernel<<<(unsigned)((width * nrhs + 255) / 256), 256, 0, st>>>(X, Y, n, r0, width, nrhs);
+  UPDES_LAUNCH_CHECK();
+  return 0;
 }

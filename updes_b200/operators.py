@@ -596,3 +596,24 @@ def pde_solver_jit(diff_operator, rhs_operator, cloud, boundary_conditions, rbf,
     """operators.py:650-683: boundary callables are turned into arrays first."""
     bc = boundary_conditions_func_to_arr(boundary_conditions, cloud)
     return pde_solver_jit_with_bc(diff_operator, rhs_operator, cloud, bc, rbf, max_degree, diff_args, rhs_args)
+
+
+def pde_multi_solver(diff_operators, rhs_operators, cloud, boundary_conditions, rbf, max_degree, nb_iters=10, tol=1e-6,
+                     diff_args=None, rhs_args=None):
+    """Fixed-count Picard iteration over coupled scalar PDEs (reference operators.py:696-771): each sweep
+    solves every equation with the latest values of all unknowns as leading ``diff_args``.  Pure host
+    loop around ``pde_solver_jit_with_bc``; ``tol`` is accepted and ignored, as in the reference."""
+    n = len(diff_operators)
+    assert n == len(rhs_operators) == len(boundary_conditions), \
+        "The number of differential operators must match the number of right-hand side operators"
+    bcs = []
+    for bc in boundary_conditions:
+        bcs.append(boundary_conditions_func_to_arr(bc, cloud))
+    sols_vals = [np.asarray(v, dtype=np.float64) for v in diff_args[0][:n]]
+    sols = None
+    for _ in range(nb_iters):
+        sols = [pde_solver_jit_with_bc(diff_operators[i], rhs_operators[i], cloud, bcs[i], rbf, max_degree,
+                                       diff_args=sols_vals + list(diff_args[i][n:]),
+                                       rhs_args=None if rhs_args is None else rhs_args[i]) for i in range(n)]
+        sols_vals = [s_.vals for s_ in sols]
+    return sols
