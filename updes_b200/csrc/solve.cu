@@ -50,9 +50,24 @@ tri_step_kernel(const double *LU, long long ld, long long n, long long k0, long 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARPS = STEP_THREADS / 32;
   // ---- A. stage T and the rhs block ------------------------------------------------------------
-  for (int r = warp; r < nb; r += NWARPS) {
-    const double *src = LU + (k0 + r) * ld + c0;
-    for (int c = lane; c < nb; c += 32) T[r * (SB + 1) + c] = src[c];
+  if (nb == SB) {
+    // 32 warps x 4 rows: issue all 16 loads of a warp before the first store (latency-bound otherwise)
+    double v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const double *src = LU + (k0 + warp + u * NWARPS) * ld + c0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[u][q] = src[lane + 32 * q];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) T[(warp + u * NWARPS) * (SB + 1) + lane + 32 * q] = v[u][q];
+  } else {
+    for (int r = warp; r < nb; r += NWARPS) {
+      const double *src = LU + (k0 + r) * ld + c0;
+      for (int c = lane; c < nb; c += 32) T[r * (SB + 1) + c] = src[c];
+    }
   }
   for (int t = tid; t < nrhs * SB; t += STEP_THREADS) {
     const int f = t / SB, c = t % SB;
