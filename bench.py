@@ -293,7 +293,7 @@ def run_gpu_arm(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json"))).get("dgemm_traffic_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "dgemm_sub_kernel<128> (DMMA m8n8k4 + TMA), %d launches/step" % (g_cnt // max(args.steps, 1)),
+    roofline = {"kernel": "dgemm_sub_kernel (DMMA m8n8k4 + TMA; <64,4> ping-pong for wide updates), %d launches/step" % (g_cnt // max(args.steps, 1)),
                 "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm_tf / fp64_peak,
                 "traffic": traffic, "peak_source": peak_src, "share_of_step": g_ms / ms_total}
     breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] // max(args.steps, 1)} for k, v in prof.items()}
@@ -444,7 +444,7 @@ def run_gpu_arm_distributed(args, world, rank, local, nx):
                         "seconds_per_step": e2e_s, "api": "updes_b200.pde_solver_jit on every rank (numpy in, numpy out)",
                         "max_err_vs_analytic": float(np.max(np.abs(sol.vals - exact)))},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"kernel": "dgemm_sub_kernel<128> on rank 0", "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak,
+                "roofline": {"kernel": "dgemm_sub_kernel (DMMA m8n8k4 + TMA) on rank 0", "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": gemm_tf / fp64_peak, "traffic": None,
                              "share_of_step": g_ms / (ms_step * args.steps),
                              "peak_source": "raw DMMA issue rate per GPU, profiles/r01_ceilings.json"},

@@ -30,3 +30,15 @@ def advdiff_op(lib, dt=1e-4, vel=(100.0, 0.0), k=0.08, dot=np.dot):
         lap = lib.nodal_laplacian(x, center, rbf, monomial)
         return (val / dt) + dot(np.asarray(vel), grad) - k * lap
     return op
+
+
+def cloud_from_golden(name):
+    """Cloud rebuilt from a tests/golden/*.npz written by tests/golden/make_golden.py."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    names = [str(v) for v in g["facet_names"]]
+    sizes = [int(v) for v in g["facet_sizes"]]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    facet_nodes = {nm: g["facet_nodes"][offs[k]:offs[k + 1]].tolist() for k, nm in enumerate(names)}
+    facet_types = {nm: str(t) for nm, t in zip(names, g["facet_types"])}
+    return u.Cloud.from_arrays(g["sorted_nodes"], g["counts"], g["Np"], facet_types, facet_nodes, g["sorted_outward_normals"]), g

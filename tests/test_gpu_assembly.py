@@ -4,7 +4,7 @@ import pytest
 
 import updes_b200 as u
 from updes_b200 import assembly as asm
-from helpers import CONFIG1_FACETS, CONFIG2_FACETS, rel_err_rowscaled
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, cloud_from_golden, rel_err_rowscaled
 
 pytestmark = pytest.mark.gpu
 
@@ -134,3 +134,40 @@ def test_eval_jets_and_apply(oracle):
     got = asm.apply_rows(rows, "polyharmonic", 1, M, c).cpu().numpy()
     want = (K[:, :N + M] @ c.T).T.cpu().numpy()
     assert np.max(np.abs(got - want)) <= 1e-11 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("tag", ["vel", "phi"])
+def test_config3_gmsh_cloud_blocks(oracle, tag):
+    """Config 3: the reference's mesh.msh cloud (N = 1385, approximate GMSH normals) at native size, with
+    the Navier-Stokes momentum operator U.grad - lap/Re (fields = u, v; demos/NavierStokes/30_...:61-65)
+    and the pressure-correction Laplacian (:89-90).  Cloud arrays come from tests/golden/."""
+    cloud, _ = cloud_from_golden("mesh_msh_cloud_%s.npz" % tag)
+    assert (cloud.N, cloud.Ni) == (1385, 1227)
+    rng = np.random.default_rng(8)
+    uu, vv = rng.normal(size=cloud.N), rng.normal(size=cloud.N)
+
+    def ns(x, center, rbf, monomial, fields):
+        U = np.array([fields[0], fields[1]])
+        return u.dot(U, u.nodal_gradient(x, center, rbf, monomial)) - u.nodal_laplacian(x, center, rbf, monomial) / 100.0
+
+    lap = lambda x, center, rbf, monomial, fields: u.nodal_laplacian(x, center, rbf, monomial)
+    for op, args, kind, param, deg in [(ns, [uu, vv], "polyharmonic", 1, 1), (lap, None, "polyharmonic", 1, 1),
+                                       (ns, [uu, vv], "thin_plate", 3, 4)]:
+        from functools import partial
+        rbf = partial(getattr(u, kind), a=param)
+        coef, coef_p = u.lower_diff_operator(op, cloud, rbf, args)
+        M = u.compute_nb_monomials(deg, 2)
+        got = _assemble_K(cloud, kind, param, M, coef)
+        want = oracle.assemble_K(cloud, kind, param, M, coef)
+        assert rel_err_rowscaled(got, want) <= 1e-12
+
+
+def test_golden_samples_through_the_cuda_path():
+    """Committed golden K samples (configs 1 and 2) reproduced by the CUDA assembly."""
+    for name, kind, coefrow, M in [("config1_30x20_phs3.npz", "polyharmonic", [0, 0, 0, 1.0, 1.0], 3),
+                                   ("config2_35x35_periodic.npz", "polyharmonic", [1e4, 100.0, 0.0, -0.08, -0.08], 1)]:
+        cloud, g = cloud_from_golden(name)
+        K = _assemble_K(cloud, kind, 1, M, np.tile(coefrow, (cloud.Ni, 1)))
+        sample = K[g["rows"]][:, g["cols"]]
+        scale = np.max(np.abs(g["K_sample"]), axis=1, keepdims=True)
+        assert np.max(np.abs(sample - g["K_sample"]) / scale) <= 1e-12

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import updes_b200 as u
-from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, laplace_op
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, cloud_from_golden, laplace_op
 
 pytestmark = pytest.mark.gpu
 
@@ -74,3 +74,41 @@ def test_gaussian_constant_field_gmsh_like(oracle):
     assert np.allclose(np.linalg.norm(g, axis=-1)[:cloud.Ni], 0, atol=1e-2)
     assert np.allclose(d[:cloud.Ni], 0, atol=1e-2)
     assert np.allclose(sol.vals[:cloud.Ni], 12.0, atol=1e-6)
+
+
+def test_config3_pressure_poisson_on_gmsh_cloud(oracle):
+    """Config 3 (phi solve of demos/NavierStokes/30_...:89-94): Laplacian with Neumann walls/inflow and a
+    Dirichlet outflow on the mesh.msh cloud; solution vs the reference formulation on the CPU."""
+    cloud, _ = cloud_from_golden("mesh_msh_cloud_phi.npz")
+    rng = np.random.default_rng(2)
+    src = rng.normal(size=cloud.Ni)
+    rhs = lambda x, centers, rbf, fields: src
+    bcs = {k: np.zeros(len(v)) for k, v in cloud.facet_nodes.items()}
+    sol = u.pde_solver_jit(laplace_op(u), rhs, cloud, bcs, partial(u.polyharmonic, a=1), 1)
+    coef = np.tile([0.0, 0.0, 0.0, 1.0, 1.0], (cloud.Ni, 1))
+    q = oracle.assemble_q(cloud, src, bcs)
+    vals, coeffs, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 1, coef, q)
+    assert _rel(sol.vals, vals) <= 1e-7, _rel(sol.vals, vals)
+    # and the system is actually solved: residual of K c = [q;0] at round-off level
+    K = oracle.assemble_K(cloud, "polyharmonic", 1, 3, coef)
+    r = K @ sol.coeffs - np.concatenate([q, np.zeros(3)])
+    assert np.max(np.abs(r)) <= 1e-13 * (np.abs(K).sum(1).max() * np.abs(sol.coeffs).max() + np.abs(q).max())
+
+
+def test_pde_multi_solver_picard_two_fields():
+    """pde_multi_solver (operators.py:696-771): two decoupled-in-the-limit equations converge to the
+    single-equation solutions after a few sweeps."""
+    cloud = u.SquareCloud(Nx=16, Ny=14, facet_types=CONFIG1_FACETS)
+    rbf = partial(u.polyharmonic, a=1)
+    zero = lambda c: 0.0
+    one = lambda c: 1.0
+    bcs = [{"South": zero, "West": zero, "North": one, "East": zero}, {"South": zero, "West": one, "North": zero, "East": zero}]
+    # eq. i:  lap(u_i) + 0 * (other field) u_i = 0  -- the coefficient depends on the other unknown through fields
+    op0 = lambda x, c, r, m, f: u.nodal_laplacian(x, c, r, m) + (0.0 * f[1]) * u.nodal_value(x, c, r, m)
+    op1 = lambda x, c, r, m, f: u.nodal_laplacian(x, c, r, m) + (0.0 * f[0]) * u.nodal_value(x, c, r, m)
+    rhs = lambda x, centers, rbf, fields: 0.0
+    u0 = [np.zeros(cloud.N), np.zeros(cloud.N)]
+    sols = u.pde_multi_solver([op0, op1], [rhs, rhs], cloud, bcs, rbf, 1, nb_iters=2, diff_args=[u0, u0], rhs_args=None)
+    ref0 = u.pde_solver_jit(laplace_op(u), rhs, cloud, bcs[0], rbf, 1)
+    ref1 = u.pde_solver_jit(laplace_op(u), rhs, cloud, bcs[1], rbf, 1)
+    assert _rel(sols[0].vals, ref0.vals) <= 1e-10 and _rel(sols[1].vals, ref1.vals) <= 1e-10

@@ -10,7 +10,7 @@ import pytest
 
 import updes_b200 as u
 from updes_b200 import assembly as asm
-from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, laplace_op
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, advdiff_op, cloud_from_golden, laplace_op
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
@@ -79,6 +79,22 @@ def test_gmsh_reader_on_generated_mesh(tmp_path, oracle):
     # inflow normals point to -x, outflow to +x
     inflow = [i - a.Ni - a.Nd for i in a.facet_nodes["Inflow"]]
     assert np.allclose(a.sorted_outward_normals[inflow], [-1.0, 0.0])
+
+
+def test_cloud_from_golden_arrays_round_trip(oracle):
+    """Cloud.from_arrays on the committed fixtures reproduces the clouds they were made from."""
+    c1, g = cloud_from_golden("config1_30x20_phs3.npz")
+    ref1 = oracle.RefSquareCloud(30, 20, CONFIG1_FACETS)       # (the original-id renumbering map is not stored)
+    assert np.array_equal(c1.sorted_nodes, ref1.sorted_nodes) and c1.facet_nodes == ref1.facet_nodes
+    assert np.array_equal(c1.sorted_outward_normals, ref1.sorted_outward_normals) and c1.node_types == ref1.node_types
+    assert (c1.N, c1.Ni, c1.Nd, c1.Nn, c1.Nr) == (ref1.N, ref1.Ni, ref1.Nd, ref1.Nn, ref1.Nr)
+    c2, _ = cloud_from_golden("config2_35x35_periodic.npz")
+    ref2 = oracle.RefSquareCloud(35, 35, CONFIG2_FACETS, noise_seed=7)
+    assert np.array_equal(c2.sorted_nodes, ref2.sorted_nodes) and c2.Np == ref2.Np and c2.facet_nodes == ref2.facet_nodes
+    assert np.array_equal(c2.sorted_outward_normals, ref2.sorted_outward_normals) and c2.node_types == ref2.node_types
+    c3, _ = cloud_from_golden("mesh_msh_cloud_vel.npz")
+    assert (c3.N, c3.Ni, c3.Nd, c3.Nn) == (1385, 1227, 109, 49)                     # SURVEY section 4
+    assert {k: len(v) for k, v in c3.facet_nodes.items()} == {"Wall": 44, "Inflow": 49, "Outflow": 49, "Blowing": 8, "Suction": 8}
 
 
 def test_rbf_identification():

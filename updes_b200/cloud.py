@@ -74,6 +74,33 @@ class Cloud:
             self.sorted_outward_normals = np.zeros((0, 2))
             self.outward_normals = {}
 
+    @classmethod
+    def from_arrays(cls, sorted_nodes, counts, Np, facet_types, facet_nodes, sorted_outward_normals):
+        """Cloud from already-renumbered arrays (user-supplied point sets, or clouds built elsewhere).
+
+        ``counts`` = (N, Ni, Nd, Nn, Nr); ``facet_types`` must already carry the reference's suffix on
+        periodic types; ``facet_nodes`` maps facet -> sorted node ids; normals are indexed
+        ``[i - Ni - Nd]`` as in the reference (cloud.py:407-408)."""
+        self = cls.__new__(cls)
+        Cloud.__init__(self, {}, support_size="max")
+        self.N, self.Ni, self.Nd, self.Nn, self.Nr = (int(c) for c in counts)
+        self.Np = [int(v) for v in Np]
+        self.facet_types = dict(facet_types)
+        self.facet_precedence = {k: i for i, k in enumerate(self.facet_types)}
+        self.facet_nodes = {k: [int(i) for i in v] for k, v in facet_nodes.items()}
+        self.sorted_nodes = np.ascontiguousarray(sorted_nodes, dtype=np.float64)
+        self.sorted_outward_normals = np.ascontiguousarray(sorted_outward_normals, dtype=np.float64).reshape(-1, 2)
+        start = self.Ni + self.Nd
+        self.outward_normals = {start + k: self.sorted_outward_normals[k] for k in range(len(self.sorted_outward_normals))}
+        types = ["i"] * self.Ni + ["d"] * self.Nd + ["n"] * self.Nn + ["r"] * self.Nr
+        types += ["p"] * (self.N - len(types))
+        for f, ids in self.facet_nodes.items():
+            for i in ids:
+                types[i] = self.facet_types[f]
+        self.node_types = dict(enumerate(types))
+        self.renumbering_map = {i: i for i in range(self.N)}
+        return self
+
     @property
     def nodes(self):
         """dict new id -> coordinates (reference attribute ``Cloud.nodes`` after renumbering)."""
