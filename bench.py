@@ -81,8 +81,24 @@ def _fast_ref_cloud(nx):
     return u.SquareCloud(Nx=nx, Ny=nx, facet_types=FACETS)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def blas_threads():
     try:
+        import numpy  # noqa: F401  (make sure the BLAS is loaded before asking)
+        import scipy.linalg  # noqa: F401
         from threadpoolctl import threadpool_info
         return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
@@ -95,6 +111,7 @@ def run_reference_arm(args):
         return
     from oracle import oracle as O
     O.build()
+    use_all_host_threads()
     nx = args.cpu_nx
     for _ in range(args.warmup):
         cpu_reference_pass(min(nx, 30))
@@ -307,6 +324,7 @@ def run_gpu_arm(args):
     if world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.build()
+        use_all_host_threads()
         cpu_reference_pass(30)
         dt, n_s, cerr = cpu_reference_pass(args.cpu_nx)
         cpu = {"value": lu_flops(n_s) / dt * 1e-12, "unit": UNIT, "cores": blas_threads(), "kind": "port",
