@@ -114,7 +114,8 @@ int updes_lu_destroy(UpdesLU *handle);
  * row k was exchanged with row ipiv[k]); info (device int32): 0 or 1-based first zero pivot. */
 int updes_lu_factor(UpdesLU *handle, double *K, int32_t *ipiv, int32_t *info, void *stream);
 /* Solve K X = B for nrhs right-hand sides using the factors.  B is [nrhs][ldb] (each
- * right-hand side contiguous, ldb >= n), overwritten by X.  transpose != 0 solves K^T X = B. */
+ * right-hand side contiguous, ldb >= n), overwritten by X.  transpose != 0 solves K^T X = B (adjoint
+ * solves; same factors: U^T w = b, L^T z = w, x = P^T z).  Use the handle that factored. */
 int updes_lu_solve(UpdesLU *handle, const double *LU, const int32_t *ipiv, double *B,
                    int64_t ldb, int nrhs, int transpose, void *stream);
 
@@ -135,6 +136,8 @@ int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t 
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule: 0 = one 128x128 CTA per SM, 1 = ping-pong (two 128x64 CTAs per SM) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
+/* triangular solves: 1 = persistent pipelined sweeps (default), 0 = one launch per 128-row block */
+int updes_lu_set_solve_variant(UpdesLU *handle, int variant);
 /* test hook: rows the 32-wide register-resident panel holds (0 = default 148*640); smaller values
  * force the 16- / 8-wide base panels used for panels taller than 94 720 / 189 440 rows */
 int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows);

@@ -92,12 +92,16 @@ def test_lu_tall_panel_paths(cap):
     assert (K[:, :n].cpu() - lu_ref).abs().max().item() <= 1e-10 * lu_ref.abs().max().item()
 
 
-@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 1), (2051, 5)])
-def test_lu_solve(n, nrhs):
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 1), (2051, 5), (128, 2), (129, 1), (20000, 2)])
+def test_lu_solve(n, nrhs, variant):
+    """Triangular solves: variant 1 = persistent pipelined sweeps (one cooperative launch per direction),
+    variant 0 = one launch per 128-row block."""
     import torch
     from updes_b200.linalg import LUFactorization
-    A, K = _matrix(n, seed=10 + n)
+    A, K = _matrix(n, seed=10 + n, dominant=(n >= 20000))
     lu = LUFactorization(K, n).factor()
+    lu.set_solve_variant(variant)
     g = torch.Generator().manual_seed(1)
     B = torch.randn((nrhs, n), generator=g, dtype=torch.float64)
     X = lu.solve(B.cuda().clone()).cpu()
@@ -105,6 +109,22 @@ def test_lu_solve(n, nrhs):
     err = (X - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 1e-9, err
     res = (A @ X.T - B.T).abs().max().item() / (A.abs().max().item() * X.abs().max().item() * n)
+    assert res <= 1e-14, res
+
+
+@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 2), (2051, 5), (129, 1)])
+def test_lu_solve_transposed(n, nrhs):
+    """K^T X = B with the factors of K (adjoint solves)."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    A, K = _matrix(n, seed=30 + n)
+    lu = LUFactorization(K, n).factor()
+    g = torch.Generator().manual_seed(2)
+    B = torch.randn((nrhs, n), generator=g, dtype=torch.float64)
+    X = lu.solve(B.cuda().clone(), transpose=True).cpu()
+    ref = torch.linalg.solve(A.T, B.T).T
+    assert (X - ref).abs().max().item() / ref.abs().max().item() <= 1e-9
+    res = (A.T @ X.T - B.T).abs().max().item() / (A.abs().max().item() * X.abs().max().item() * n)
     assert res <= 1e-14, res
 
 

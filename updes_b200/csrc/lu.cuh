@@ -33,6 +33,10 @@ struct UpdesLU {
   unsigned int barrier_count = 0;  // host mirror of the counter after all enqueued panels
   unsigned int *gemm_counters = nullptr;   // ring of per-launch tile counters (dynamic scheduler)
   unsigned long long gemm_launch_id = 0;
+  int solve_variant = 1;           // 1: persistent pipelined sweeps (default); 0: one launch per 128-row block
+  unsigned int *sweep_flags = nullptr;   // [ceil(n/128)] publication flags of the persistent sweep
+  unsigned int sweep_epoch = 0;
+  int *sweep_err = nullptr;
   int32_t *perm = nullptr;         // [n] row permutation of the last factorisation (for solves)
   double *xbuf = nullptr;          // solve scratch
 };

@@ -65,6 +65,11 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   if (e == cudaSuccess) e = cudaMemset(h->barrier, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&h->gemm_counters, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
   if (e == cudaSuccess) e = cudaMemset(h->gemm_counters, 0, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
+  const size_t nflags = (size_t)((n + 127) / 128) + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_flags, sizeof(unsigned int) * nflags);
+  if (e == cudaSuccess) e = cudaMemset(h->sweep_flags, 0, sizeof(unsigned int) * nflags);
+  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_err, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->sweep_err, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
   if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * n * 8);   // X and Y, 4 right-hand sides each
   if (e != cudaSuccess) {
@@ -78,7 +83,7 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
 extern "C" int updes_lu_destroy(UpdesLU *h) {
   if (!h) return 0;
   cudaFree(h->cand); cudaFree(h->top); cudaFree(h->candval); cudaFree(h->candrow);
-  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters);
+  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters); cudaFree(h->sweep_flags); cudaFree(h->sweep_err);
   delete h;
   return 0;
 }

@@ -9,6 +9,14 @@
 #include "lu.cuh"
 
 namespace updes {
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+}  // namespace updes
+
+namespace updes {
 
 constexpr int SB = 128;
 constexpr int SOLVE_MAX_RHS = 4;
@@ -170,6 +178,372 @@ tri_step_kernel(const double *LU, long long ld, long long n, long long k0, long 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Transposed solves  K^T x = b  with the same factors (adjoint / VJP of the solve).
+//   P K = L U  =>  K^T = U^T L^T P :  U^T w = b (forward, lower with diagonal),
+//                                     L^T z = w (backward, unit upper),  x[perm[i]] = z[i].
+// One launch per 128-row block: every CTA stages the diagonal block, solves its transpose redundantly,
+// then updates its share of the remaining unknowns.  With row-major factors the update
+// X[i] -= sum_c F[k0+c][i] w_c runs one thread per column i (128 coalesced row reads).
+// FWD = true: U^T (forward);  FWD = false: L^T (backward, unit diagonal).
+// ------------------------------------------------------------------------------------------------
+template <bool FWD>
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+tri_step_t_kernel(const double *LU, long long ld, long long n, long long k0, int nb, long long i0, long long i1,
+                  double *X, double *Yout, int nrhs) {
+  extern __shared__ double sm[];
+  double *T = sm;
+  double *xs = sm + SB * (SB + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = STEP_THREADS / 32;
+  for (int r = warp; r < SB; r += NWARPS) {
+    const double *src = LU + (k0 + r) * ld + k0;
+    for (int c = lane; c < SB; c += 32) T[r * (SB + 1) + c] = (r < nb && c < nb) ? src[c] : (r == c ? 1.0 : 0.0);
+  }
+  for (int t = tid; t < nrhs * SB; t += STEP_THREADS) {
+    const int f = t / SB, c = t % SB;
+    xs[f * SB + c] = c < nb ? X[f * n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  // solve T^T y = xs.  FWD: T upper (U block), T^T lower with diagonal -> ascending;
+  //                   !FWD: T unit lower (L block), T^T unit upper -> descending.
+  for (int q = 0; q < 4; q++) {
+    const int sb = FWD ? q : 3 - q;
+    const int base = sb * 32;
+    if (warp == 0) {
+      for (int f = 0; f < nrhs; f++) {
+        double x = xs[f * SB + base + lane];
+        if (FWD) {
+          for (int c = 0; c < 32; c++) {
+            if (lane == c) x = x / T[(base + c) * (SB + 1) + base + c];
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane > c) x = fma(-T[(base + c) * (SB + 1) + base + lane], xc, x);     // T^T[lane][c] = T[c][lane]
+          }
+        } else {
+          for (int c = 31; c >= 0; c--) {
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane < c) x = fma(-T[(base + c) * (SB + 1) + base + lane], xc, x);
+          }
+        }
+        xs[f * SB + base + lane] = x;
+      }
+    }
+    __syncthreads();
+    const int rbeg = FWD ? base + 32 : 0, rend = FWD ? SB : base;
+    for (int t = tid; t < (rend - rbeg) * nrhs; t += STEP_THREADS) {
+      const int f = t / (rend - rbeg), r = rbeg + t % (rend - rbeg);
+      double v = xs[f * SB + r];
+      for (int c = 0; c < 32; c++) v = fma(-T[(base + c) * (SB + 1) + r], xs[f * SB + base + c], v);
+      xs[f * SB + r] = v;
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0)
+    for (int t = tid; t < nrhs * nb; t += STEP_THREADS) {
+      const int f = t / nb, c = t % nb;
+      Yout[f * n + k0 + c] = xs[f * SB + c];
+    }
+  // remaining unknowns i in [i0, i1): X[i] -= sum_c F[k0+c][i] * y_c
+  for (long long i = i0 + (long long)blockIdx.x * STEP_THREADS + tid; i < i1; i += (long long)gridDim.x * STEP_THREADS) {
+    const double *col = LU + k0 * ld + i;
+    double acc[SOLVE_MAX_RHS] = {0, 0, 0, 0};
+    for (int c0 = 0; c0 < nb; c0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (c0 + u < nb) ? col[(long long)(c0 + u) * ld] : 0.0;
+      for (int f = 0; f < nrhs; f++)
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[f] = fma(v[u], xs[f * SB + c0 + u], acc[f]);
+    }
+    for (int f = 0; f < nrhs; f++) X[f * n + i] -= acc[f];
+  }
+}
+
+__global__ void scatter_rows_kernel(const double *Z, long long n, int nrhs, const int32_t *perm, double *B, long long ldb) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = perm[i];
+  for (int f = 0; f < nrhs; f++) B[f * ldb + p] = Z[f * n + i];
+}
+
+__global__ void copy_in_kernel(const double *B, long long ldb, int nrhs, long long n, double *X) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int f = 0; f < nrhs; f++) X[f * n + i] = B[f * ldb + i];
+}
+
+static int solve_chunk_transposed(UpdesLU *h, const double *LU, double *X, double *Y, int nrhs, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_step_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM));
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_step_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM));
+    attr = true;
+  }
+  const long long n = h->n, ld = h->ld;
+  const long long nblk = (n + SB - 1) / SB;
+  auto grid_for = [&](long long cols) {
+    const long long want = (cols + STEP_THREADS - 1) / STEP_THREADS;
+    return (int)(want < 1 ? 1 : (want > h->num_sms ? h->num_sms : want));
+  };
+  for (long long kb = 0; kb < nblk; kb++) {                 // U^T w = b : X -> Y
+    const long long k0 = kb * SB;
+    const int nb = (int)((n - k0) < SB ? (n - k0) : SB);
+    tri_step_t_kernel<true><<<grid_for(n - k0 - nb), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, nb, k0 + nb, n, X, Y, nrhs);
+    UPDES_LAUNCH_CHECK();
+  }
+  for (long long kb = nblk - 1; kb >= 0; kb--) {            // L^T z = w : Y -> X
+    const long long k0 = kb * SB;
+    const int nb = (int)((n - k0) < SB ? (n - k0) : SB);
+    tri_step_t_kernel<false><<<grid_for(k0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, nb, 0, k0, Y, X, nrhs);
+    UPDES_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent pipelined sweep (default): ONE cooperative launch per sweep direction.
+//
+// The rows are cut into 128-row blocks owned cyclically by the resident CTAs (block j -> CTA j % G).
+// A CTA applies every block step's update to the rows it owns; the owner of the NEXT diagonal block
+// updates that block first, solves it at once (its diagonal 128x128 tile was staged in shared memory
+// while it was still waiting) and publishes the solution behind a flag, and only then catches up with
+// the rest of its rows.  The serial chain per step is therefore: flag -> 128 rows of update -> warp
+// substitution -> publish (a few microseconds), while the other ~147 CTAs stream L / U at HBM rate in
+// the background.  Diagonal 32x32 sub-blocks are held in registers (one row per lane) during the
+// substitution so the chain is one shuffle + one FMA per column.
+// ------------------------------------------------------------------------------------------------
+constexpr int SWEEP_THREADS = 512;
+constexpr size_t SWEEP_SMEM = sizeof(double) * (SB * (SB + 1) + 2 * SOLVE_MAX_RHS * SB);
+
+struct SweepParams {
+  const double *LU;
+  long long ld, n;
+  long long cbase;          // column of diagonal block kb = cbase + 128*kb
+  int kb_begin, kb_end;     // block steps [kb_begin, kb_end) of the 128-row partition of [0, n)
+  double *X, *Y;            // running right-hand side (updated in place) / solved blocks
+  int nrhs;
+  unsigned int *flags;      // [ceil(n/128)]: == epoch once block kb's solution is in Y
+  unsigned int epoch;
+  int *err;                 // set to 1 if a wait timed out (never expected)
+};
+
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool UPPER>
+__device__ __forceinline__ void sweep_stage_T(const SweepParams &P, int kb, double *T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = SWEEP_THREADS / 32;
+  const long long k0 = 128LL * kb;
+  const int nb = (int)min(128LL, P.n - k0);
+  const double *base = P.LU + k0 * P.ld + P.cbase + k0;
+  if (nb == SB) {
+#pragma unroll
+    for (int g = 0; g < SB / NW; g += 4) {
+      double v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[u][q] = base[(long long)(warp + (g + u) * NW) * P.ld + lane + 32 * q];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) T[(warp + (g + u) * NW) * (SB + 1) + lane + 32 * q] = v[u][q];
+    }
+  } else {
+    for (int r = warp; r < SB; r += NW)
+      for (int c = lane; c < SB; c += 32)
+        T[r * (SB + 1) + c] = (r < nb && c < nb) ? base[(long long)r * P.ld + c] : (r == c ? 1.0 : 0.0);
+  }
+}
+
+// Solve the staged diagonal block against X[block kb]; result in xs (shared) and Y; publish the flag.
+template <bool UPPER>
+__device__ __forceinline__ void sweep_solve_block(const SweepParams &P, int kb, const double *T, double *xs) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long k0 = 128LL * kb;
+  const int nb = (int)min(128LL, P.n - k0);
+  for (int t = tid; t < P.nrhs * SB; t += SWEEP_THREADS) {
+    const int f = t / SB, c = t % SB;
+    xs[f * SB + c] = c < nb ? P.X[f * P.n + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  for (int q = 0; q < 4; q++) {
+    const int sb = UPPER ? 3 - q : q;
+    const int base = sb * 32;
+    if (warp == 0) {
+      double trow[32];
+#pragma unroll
+      for (int c = 0; c < 32; c++) trow[c] = T[(base + lane) * (SB + 1) + base + c];
+      double rd = 1.0;
+      if (UPPER) {
+        double d = trow[0];
+#pragma unroll
+        for (int c = 1; c < 32; c++) d = lane == c ? trow[c] : d;
+        rd = 1.0 / d;
+      }
+      for (int f = 0; f < P.nrhs; f++) {
+        double x = xs[f * SB + base + lane];
+        if (!UPPER) {
+#pragma unroll
+          for (int c = 0; c < 31; c++) {
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane > c) x = fma(-trow[c], xc, x);
+          }
+        } else {
+#pragma unroll
+          for (int c = 31; c >= 0; c--) {
+            if (lane == c) x *= rd;
+            const double xc = __shfl_sync(0xffffffffu, x, c);
+            if (lane < c) x = fma(-trow[c], xc, x);
+          }
+        }
+        xs[f * SB + base + lane] = x;
+      }
+    }
+    __syncthreads();
+    // remaining sub-blocks of this diagonal block: 4 threads per row, 8 columns each
+    const int rbeg = UPPER ? 0 : base + 32, rend = UPPER ? base : SB;
+    const int nrow = rend - rbeg;
+    for (int t = tid; t < nrow * 4 * P.nrhs; t += SWEEP_THREADS) {
+      const int part = t & 3, rr = (t >> 2) % nrow, f = (t >> 2) / nrow;
+      const int r = rbeg + rr;
+      const double *trow = T + r * (SB + 1) + base + part * 8;
+      const double *xv = xs + f * SB + base + part * 8;
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) v = fma(trow[c], xv[c], v);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (part == 0) xs[f * SB + r] -= v;
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < P.nrhs * nb; t += SWEEP_THREADS) {
+    const int f = t / nb, c = t % nb;
+    P.Y[f * P.n + k0 + c] = xs[f * SB + c];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release_u32(P.flags + kb, P.epoch);
+}
+
+// X[rows of block j] -= LU[rows of block j][columns of block kb] * xs   (this CTA owns block j)
+__device__ __forceinline__ void sweep_update_block(const SweepParams &P, int j, int kb, const double *xs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = SWEEP_THREADS / 32;
+  constexpr int RW = SB / NW;                 // rows per warp (8)
+  const long long r0 = 128LL * j, k0 = 128LL * kb;
+  const int nbj = (int)min(128LL, P.n - r0), nb = (int)min(128LL, P.n - k0);
+  const double *base = P.LU + r0 * P.ld + P.cbase + k0;
+  if (nb == SB) {
+    double2 v0[RW], v1[RW];
+#pragma unroll
+    for (int u = 0; u < RW; u++) {
+      const int r = warp + u * NW;
+      if (r < nbj) {
+        const double *row = base + (long long)r * P.ld;
+        v0[u] = *reinterpret_cast<const double2 *>(row + 2 * lane);
+        v1[u] = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
+      } else {
+        v0[u] = make_double2(0.0, 0.0); v1[u] = v0[u];
+      }
+    }
+    for (int f = 0; f < P.nrhs; f++) {
+      const double *xf = xs + f * SB;
+      const double x0 = xf[2 * lane], x1 = xf[2 * lane + 1], x2 = xf[64 + 2 * lane], x3 = xf[64 + 2 * lane + 1];
+      double a[RW];
+#pragma unroll
+      for (int u = 0; u < RW; u++) a[u] = fma(v1[u].y, x3, fma(v1[u].x, x2, fma(v0[u].y, x1, v0[u].x * x0)));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int u = 0; u < RW; u++) a[u] += __shfl_xor_sync(0xffffffffu, a[u], off);
+      if (lane < RW) {
+        double mine = a[0];
+#pragma unroll
+        for (int u = 1; u < RW; u++) mine = lane == u ? a[u] : mine;
+        const int r = warp + lane * NW;
+        if (r < nbj) P.X[f * P.n + r0 + r] -= mine;
+      }
+    }
+  } else {
+    for (int r = warp; r < nbj; r += NW) {
+      const double *row = base + (long long)r * P.ld;
+      for (int f = 0; f < P.nrhs; f++) {
+        double a = 0.0;
+        for (int c = lane; c < nb; c += 32) a = fma(row[c], xs[f * SB + c], a);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) P.X[f * P.n + r0 + r] -= a;
+      }
+    }
+  }
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1) tri_sweep_kernel(SweepParams P) {
+  extern __shared__ double sm[];
+  double *T = sm;                                   // [SB][SB+1]
+  double *xsbuf = sm + SB * (SB + 1);               // [2][SOLVE_MAX_RHS][SB]
+  const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
+  const int nblk = (int)((P.n + SB - 1) / SB);
+  const int nsteps = P.kb_end - P.kb_begin;
+  int cur = 0;
+  bool have_local = false;
+  {
+    const int kb0 = UPPER ? P.kb_end - 1 : P.kb_begin;
+    if (kb0 % G == me) {                            // the first diagonal block has no predecessor
+      sweep_stage_T<UPPER>(P, kb0, T);
+      __syncthreads();
+      sweep_solve_block<UPPER>(P, kb0, T, xsbuf);
+      have_local = true;
+    }
+  }
+  for (int t = 0; t < nsteps; t++) {
+    const int kb = UPPER ? P.kb_end - 1 - t : P.kb_begin + t;
+    const int kn = UPPER ? kb - 1 : kb + 1;
+    const bool next_mine = (t + 1 < nsteps) && (kn % G == me);
+    double *xk = xsbuf + cur * SOLVE_MAX_RHS * SB;
+    if (next_mine) sweep_stage_T<UPPER>(P, kn, T);  // before waiting: hides the staging latency
+    if (!have_local) {
+      if (tid == 0) {
+        unsigned int polls = 0;
+        while (ld_acquire_u32(P.flags + kb) != P.epoch) {
+          if (++polls > (1u << 24)) { atomicExch(P.err, 1); break; }
+        }
+      }
+      __syncthreads();
+      const int nb = (int)min(128LL, P.n - 128LL * kb);
+      for (int i = tid; i < P.nrhs * SB; i += SWEEP_THREADS) {
+        const int f = i / SB, c = i % SB;
+        xk[f * SB + c] = c < nb ? __ldcg(P.Y + f * P.n + 128LL * kb + c) : 0.0;
+      }
+    }
+    __syncthreads();
+    have_local = false;
+    if (next_mine) {
+      sweep_update_block(P, kn, kb, xk);
+      __threadfence_block();
+      __syncthreads();
+      sweep_solve_block<UPPER>(P, kn, T, xsbuf + (cur ^ 1) * SOLVE_MAX_RHS * SB);
+      have_local = true;
+    }
+    // the rest of my rows (forward: blocks after kb; backward: blocks before kb)
+    if (!UPPER) {
+      int j = kb + 1 + (((me - (kb + 1)) % G) + G) % G;
+      for (; j < nblk; j += G)
+        if (!(next_mine && j == kn)) sweep_update_block(P, j, kb, xk);
+    } else {
+      for (int j = me; j < kb; j += G)
+        if (!(next_mine && j == kn)) sweep_update_block(P, j, kb, xk);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
 static int ensure_solve_attrs() {
   static bool attr = false;
   if (!attr) {
@@ -210,12 +584,42 @@ int tri_block_sweep(int num_sms, const double *LU, long long ld, long long n, bo
   return 0;
 }
 
+// One cooperative launch: block steps [kb_begin, kb_end) of the factor stored at `LU` (diagonal block
+// kb at column cbase + 128 kb).  X is the running right-hand side, Y receives the solved blocks.
+int tri_sweep_persistent(UpdesLU *h, const double *LU, long long ld, long long n, bool upper, long long cbase,
+                         int kb_begin, int kb_end, double *X, double *Y, int nrhs, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM));
+    attr = true;
+  }
+  if (kb_end <= kb_begin) return 0;
+  SweepParams P;
+  P.LU = LU; P.ld = ld; P.n = n; P.cbase = cbase; P.kb_begin = kb_begin; P.kb_end = kb_end; P.X = X; P.Y = Y;
+  P.nrhs = nrhs; P.flags = h->sweep_flags; P.epoch = ++h->sweep_epoch; P.err = h->sweep_err;
+  const int nblk = (int)((n + SB - 1) / SB);
+  const int grid = nblk < h->num_sms ? nblk : h->num_sms;
+  void *args[] = {&P};
+  cudaError_t e = upper ? cudaLaunchCooperativeKernel((void *)tri_sweep_kernel<true>, dim3(grid), dim3(SWEEP_THREADS), args, SWEEP_SMEM, st)
+                        : cudaLaunchCooperativeKernel((void *)tri_sweep_kernel<false>, dim3(grid), dim3(SWEEP_THREADS), args, SWEEP_SMEM, st);
+  if (e != cudaSuccess) return (int)e;
+  ++g_launch_count;
+  return 0;
+}
+
 // whole solve on one GPU: X = P b in xbuf[0]; forward sweep X -> Y; backward sweep Y -> X
 static int solve_chunk(UpdesLU *h, const double *LU, double *X, double *Y, int nrhs, cudaStream_t st) {
   const long long n = h->n;
-  int rc = tri_block_sweep(h->num_sms, LU, h->ld, n, false, 0, 0, n, X, Y, nrhs, st);
+  const int nblk = (int)((n + SB - 1) / SB);
+  if (h->solve_variant == 0) {
+    int rc = tri_block_sweep(h->num_sms, LU, h->ld, n, false, 0, 0, n, X, Y, nrhs, st);
+    if (rc) return rc;
+    return tri_block_sweep(h->num_sms, LU, h->ld, n, true, 0, 0, n, Y, X, nrhs, st);
+  }
+  int rc = tri_sweep_persistent(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, nrhs, st);
   if (rc) return rc;
-  return tri_block_sweep(h->num_sms, LU, h->ld, n, true, 0, 0, n, Y, X, nrhs, st);
+  return tri_sweep_persistent(h, LU, h->ld, n, true, 0, 0, nblk, Y, X, nrhs, st);
 }
 
 }  // namespace updes
@@ -229,12 +633,21 @@ extern "C" int updes_lu_solve(UpdesLU *h, const double *LU, const int32_t *ipiv,
   if (!B) return -4;
   if (ldb < h->n) return -5;
   if (nrhs <= 0) return 0;
-  if (transpose) return -7;   // K^T solves: not built yet
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = h->n;
   for (int f0 = 0; f0 < nrhs; f0 += SOLVE_MAX_RHS) {
     const int nf = (nrhs - f0) < SOLVE_MAX_RHS ? (nrhs - f0) : SOLVE_MAX_RHS;
     double *Bf = B + (long long)f0 * ldb;
+    if (transpose) {
+      double *Xt = h->xbuf, *Yt = h->xbuf + (size_t)SOLVE_MAX_RHS * n;
+      copy_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, n, Xt);
+      UPDES_LAUNCH_CHECK();
+      int rct = solve_chunk_transposed(h, LU, Xt, Yt, nf, st);
+      if (rct) return rct;
+      scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Xt, n, nf, h->perm, Bf, ldb);
+      UPDES_LAUNCH_CHECK();
+      continue;
+    }
     gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf);
     UPDES_LAUNCH_CHECK();
     prof_begin(PROF_SOLVE, 8.0 * (double)n * (double)n, st);
@@ -285,9 +698,21 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = h->view[slot].rows;
   double *Y = h->xbuf + (size_t)SOLVE_MAX_RHS * h->n;     // scratch for the solved block
-  int rc = tri_block_sweep(h->num_sms, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, r0, c0, width, X, Y, nrhs, st);
+  int rc;
+  if (h->solve_variant != 0 && (r0 % SB) == 0)
+    rc = tri_sweep_persistent(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
+                              (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
+  else
+    rc = tri_block_sweep(h->num_sms, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, r0, c0, width, X, Y, nrhs, st);
   if (rc) return rc;
   copy_block_kernel<<<(unsigned)((width * nrhs + 255) / 256), 256, 0, st>>>(X, Y, n, r0, width, nrhs);
   UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int updes_lu_set_solve_variant(UpdesLU *handle, int variant) {
+  if (!handle) return -1;
+  if (variant < 0 || variant > 1) return -2;
+  handle->solve_variant = variant;
   return 0;
 }

@@ -40,16 +40,19 @@ class LUFactorization:
         """0, or the 1-based index of the first exactly-zero pivot (synchronises)."""
         return int(self.info.item())
 
-    def solve(self, B):
-        """Solve K X = B in place.  B: (nrhs, ldb>=n) or (n,) CUDA float64; returns B."""
+    def solve(self, B, transpose=False):
+        """Solve K X = B (or K^T X = B) in place.  B: (nrhs, ldb>=n) or (n,) CUDA float64; returns B."""
         assert self.factored
         single = B.dim() == 1
         Bm = B.view(1, -1) if single else B
         assert Bm.is_contiguous() and Bm.shape[1] >= self.n
         rc = self._lib.updes_lu_solve(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(), Bm.data_ptr(),
-                                      Bm.shape[1], Bm.shape[0], 0, _lib.stream_ptr())
+                                      Bm.shape[1], Bm.shape[0], 1 if transpose else 0, _lib.stream_ptr())
         _lib.check(rc, "updes_lu_solve")
         return B
+
+    def set_solve_variant(self, variant: int):
+        _lib.check(self._lib.updes_lu_set_solve_variant(self._handle, variant), "updes_lu_set_solve_variant")
 
     def set_panel_capacity(self, rows: int):
         _lib.check(self._lib.updes_lu_set_panel_capacity(self._handle, rows), "updes_lu_set_panel_capacity")
