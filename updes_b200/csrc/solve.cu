@@ -699,7 +699,8 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
   const long long n = h->view[slot].rows;
   double *Y = h->xbuf + (size_t)SOLVE_MAX_RHS * h->n;     // scratch for the solved block
   int rc;
-  if (h->solve_variant != 0 && (r0 % SB) == 0)
+  // the persistent kernel works on the 128-row partition of [0, n): the column block must be aligned to it
+  if (h->solve_variant != 0 && (r0 % SB) == 0 && ((width % SB) == 0 || r0 + width == n))
     rc = tri_sweep_persistent(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
                               (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
   else
