@@ -4,7 +4,7 @@ container, where /root/reference is mounted):
   config1_30x20_phs3.npz   README Laplace problem: cloud arrays, a sample of K, q, the solution of
                            the reference formulation (inv + GEMM + QR on the CPU oracle)
   config2_35x35_periodic.npz  periodic adv-diff cloud (demos/Advection/01): cloud arrays, K sample
-  mesh_msh_cloud_{vel,phi}.npz  the reference's own fixture updes/tests/data/mesh.msh parsed with the
+  mesh_msh_cloud_{vel,phi,alln}.npz  the reference's own fixture updes/tests/data/mesh.msh parsed with the
                            oracle's literal restatement of GmshCloud (sorted nodes, normals, counts,
                            facet nodes) for the two facet-type sets of demos/NavierStokes/30_...:40-41
 
@@ -54,7 +54,9 @@ np.savez_compressed(os.path.join(OUT, "config2_35x35_periodic.npz"), rows=rows, 
 
 mesh = "/root/reference/updes/tests/data/mesh.msh"
 for tag, ft in (("vel", {"Wall": "d", "Inflow": "d", "Outflow": "n", "Blowing": "d", "Suction": "d"}),
-                ("phi", {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"})):
+                ("phi", {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"}),
+                # updes/tests/test_operators.py:26 -- every facet Neumann
+                ("alln", {"Wall": "n", "Inflow": "n", "Outflow": "n", "Blowing": "n", "Suction": "n"})):
     c = O.RefGmshCloud(mesh, ft)
     np.savez_compressed(os.path.join(OUT, "mesh_msh_cloud_%s.npz" % tag), **cloud_arrays(c))
 print("golden fixtures written to", OUT)

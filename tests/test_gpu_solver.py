@@ -112,3 +112,15 @@ def test_pde_multi_solver_picard_two_fields():
     ref0 = u.pde_solver_jit(laplace_op(u), rhs, cloud, bcs[0], rbf, 1)
     ref1 = u.pde_solver_jit(laplace_op(u), rhs, cloud, bcs[1], rbf, 1)
     assert _rel(sols[0].vals, ref0.vals) <= 1e-10 and _rel(sols[1].vals, ref1.vals) <= 1e-10
+
+
+def test_reference_test_operators_on_its_own_mesh_gpu():
+    """The reference's own test (updes/tests/test_operators.py:102-103) through the CUDA path, on the
+    committed parse of its mesh.msh fixture: constant field, vanishing gradient and divergence."""
+    cloud, _ = cloud_from_golden("mesh_msh_cloud_alln.npz")
+    rbf = partial(u.gaussian, eps=10.0)
+    op = lambda x, c, r, m, f: u.nodal_value(x, c, r, m)
+    sol = u.pde_solver(op, lambda x, centers, rbf, fields: 12.0, cloud, {k: (lambda c: 0.0) for k in cloud.facet_types}, rbf, 1)
+    grads = u.gradient_vec(cloud.sorted_nodes, sol.coeffs, cloud.sorted_nodes, rbf)
+    divs = u.divergence_vec(cloud.sorted_nodes, np.stack([sol.coeffs, sol.coeffs], -1), cloud.sorted_nodes, rbf)
+    assert np.allclose(np.linalg.norm(grads, axis=-1), 0, atol=1e-2) and np.allclose(divs, 0, atol=1e-2)

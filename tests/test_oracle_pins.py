@@ -9,7 +9,7 @@ from functools import partial
 import numpy as np
 import pytest
 
-from helpers import CONFIG1_FACETS, CONFIG2_FACETS, rel_err_rowscaled
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, cloud_from_golden, rel_err_rowscaled
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -112,6 +112,23 @@ def test_reference_test_operators_known_answer(oracle):
     gy = oracle.eval_field(cloud.sorted_nodes[:cloud.Ni], cloud.sorted_nodes, coeffs, "gaussian", 10.0, "dy")
     assert np.allclose(vals[:cloud.Ni], 12.0, atol=1e-6)
     assert np.allclose(np.hypot(gx, gy), 0, atol=1e-2)
+
+
+def test_reference_test_operators_on_its_own_mesh(oracle):
+    """updes/tests/test_operators.py verbatim: GmshCloud(mesh.msh) with every facet Neumann, gaussian
+    eps=10, max_degree=1, diff = nodal_value, rhs = 12, zero Neumann data; assert |grad u| ~ 0 and
+    div(u, u) ~ 0 with atol 1e-2 (lines 102-103).  The cloud is the committed parse of that fixture."""
+    cloud, _ = cloud_from_golden("mesh_msh_cloud_alln.npz")
+    assert (cloud.N, cloud.Nd, cloud.Nn) == (1385, 0, 158)
+    coef = np.tile([1.0, 0, 0, 0, 0], (cloud.Ni, 1))
+    q = oracle.assemble_q(cloud, np.full(cloud.Ni, 12.0), {k: np.zeros(len(v)) for k, v in cloud.facet_nodes.items()})
+    vals, coeffs, _ = oracle.reference_solve(cloud, "gaussian", 10.0, 1, coef, q)
+    xy = cloud.sorted_nodes
+    gx = oracle.eval_field(xy, xy, coeffs, "gaussian", 10.0, "dx")
+    gy = oracle.eval_field(xy, xy, coeffs, "gaussian", 10.0, "dy")
+    assert np.allclose(np.hypot(gx, gy), 0, atol=1e-2)          # test_operators.py:103, first clause
+    assert np.allclose(gx + gy, 0, atol=1e-2)                   # divergence of (u, u), second clause
+    assert np.allclose(vals[:cloud.Ni], 12.0, atol=1e-6)
 
 
 def test_laplace_analytic_solution(oracle):

@@ -68,8 +68,29 @@ __global__ void init_kernel(double* p, size_t n, size_t ld, size_t rows) {
 
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
+// cuSOLVER Dgetrf alone at one (large) size: the library comparator at the headline n.
+static int getrf_only(size_t n) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  cusolverDnHandle_t so; cusolverDnCreate(&so);
+  double* A; int* ipiv; int* info; double* work; int lwork = 0;
+  CK(cudaMalloc(&A, n * n * 8)); CK(cudaMalloc(&ipiv, n * 4)); CK(cudaMalloc(&info, 4));
+  cusolverDnDgetrf_bufferSize(so, n, n, A, n, &lwork);
+  CK(cudaMalloc(&work, (size_t)lwork * 8));
+  init_kernel<<<148 * 8, 256>>>(A, n * n, n, n);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  cusolverDnDgetrf(so, n, n, A, n, work, ipiv, info);
+  CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+  float ms = time_ms(e0, e1);
+  int hinfo = -1; CK(cudaMemcpy(&hinfo, info, 4, cudaMemcpyDeviceToHost));
+  printf("{\"cusolver_getrf_n%zu\": {\"ms\": %.1f, \"tflops\": %.2f, \"info\": %d, \"lwork_doubles\": %d}}\n", n, ms,
+         2.0 / 3.0 * n * n * n / ms * 1e-9, hinfo, lwork);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   int big = argc > 1 ? atoi(argv[1]) : 16384;
+  if (argc > 2) return getrf_only((size_t)atol(argv[2]));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d,\n", prop.name, prop.multiProcessorCount, prop.clockRate);
