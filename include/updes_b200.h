@@ -136,6 +136,9 @@ int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t 
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule: 0 = one 128x128 CTA per SM, 1 = ping-pong (two 128x64 CTAs per SM) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
+/* base panels: 1 = panels of <= 10 240 rows run in one thread-block cluster (DSMEM exchange, hardware
+ * cluster barrier; default), 0 = always the grid-wide cooperative kernel */
+int updes_lu_set_panel_variant(UpdesLU *handle, int variant);
 /* triangular solves: 1 = persistent pipelined sweeps (default), 0 = one launch per 128-row block */
 int updes_lu_set_solve_variant(UpdesLU *handle, int variant);
 /* test hook: rows the 32-wide register-resident panel holds (0 = default 148*640); smaller values

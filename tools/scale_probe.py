@@ -30,10 +30,18 @@ def run(nx, detail=False):
     e0 = ev(); asm.assemble_system(rows, "polyharmonic", 1.0, M, out=K); e1 = ev(); torch.cuda.synchronize()
     t_asm = e0.elapsed_time(e1)
     lu = LUFactorization(K, n)
+    if PANEL_VARIANT is not None:
+        lu.set_panel_variant(PANEL_VARIANT)
+    lu.factor(); torch.cuda.synchronize()                      # warm-up: lazy kernel loading, attribute calls
+    asm.assemble_system(rows, "polyharmonic", 1.0, M, out=K)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
     l0 = _lib.launch_count()
     e0 = ev(); lu.factor(); e1 = ev(); torch.cuda.synchronize()
     t_lu = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
+    prof = {k: (round(_lib.profile_read(k)[0], 2), _lib.profile_read(k)[2]) for k in ("gemm", "panel", "swap", "trsm")}
+    _lib.profile_enable(False)
     xy = cloud.sorted_nodes
     q = np.zeros(n)
     north = np.asarray(cloud.facet_nodes["North"])
@@ -55,12 +63,17 @@ def run(nx, detail=False):
     out = dict(nx=nx, n=n, asm_ms=round(t_asm, 3), asm_gbs=round(8.0 * n * n / t_asm * 1e-6, 1), lu_ms=round(t_lu, 2),
                lu_tflops=round(2 / 3 * n ** 3 / t_lu * 1e-9, 2), solve_ms=round(t_solve, 3),
                solve_gbs=round(8.0 * n * n / t_solve * 1e-6, 1), launches=launches, info=lu.zero_pivot(),
-               backward_err=berr, max_err_vs_analytic=float(np.max(np.abs(vals - exact))))
+               backward_err=berr, max_err_vs_analytic=float(np.max(np.abs(vals - exact))), prof_ms_launches=prof)
     print(json.dumps(out), flush=True)
     del K, lu, rows
     torch.cuda.empty_cache()
 
 
+PANEL_VARIANT = None
+
 if __name__ == "__main__":
+    import os
+    if "PANEL_VARIANT" in os.environ:
+        PANEL_VARIANT = int(os.environ["PANEL_VARIANT"])
     for nx in [int(a) for a in sys.argv[1:]] or [64, 128]:
         run(nx)

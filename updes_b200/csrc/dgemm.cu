@@ -409,3 +409,10 @@ extern "C" int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows) {
   handle->panel_cap = rows;
   return 0;
 }
+
+extern "C" int updes_lu_set_panel_variant(UpdesLU *handle, int variant) {
+  if (!handle) return -1;
+  if (variant < 0 || variant > 1) return -2;
+  handle->panel_variant = variant;
+  return 0;
+}

@@ -217,6 +217,193 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster variant for short panels (m <= 16 x 640 rows): the CTAs of ONE thread-block cluster hold the
+// panel, candidates are exchanged through distributed shared memory and the per-column barrier is a
+// hardware cluster barrier (~0.6 us per column instead of ~5 us through global memory).  Same
+// algorithm and tie-breaking as lu_panel_kernel; two candidate buffers alternate by column parity, so
+// one cluster barrier per column is enough (a CTA can only overwrite buffer p two columns later, after
+// every CTA has passed the barrier in between, i.e. finished reading it).
+// ------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+template <int JB>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_cluster_kernel(PanelParams P) {
+  __shared__ double s_wv[32];
+  __shared__ int s_wr[32];
+  __shared__ double s_prow[JB], s_trow[JB];
+  __shared__ int s_piv;
+  // exchanged through DSMEM (double-buffered by column parity)
+  __shared__ double x_cand[2][JB], x_top[2][JB], x_cval[2];
+  __shared__ int x_crow[2];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int b = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+  const int jb = P.jb;
+  const long long row = P.r0 + (long long)b * P.rows_per_cta + tid;
+  const bool valid = tid < P.rows_per_cta && row < P.n;
+  const long long myrow = valid ? row : -1;
+
+  double a[JB];
+  if (valid) {
+    const double *src = P.K + row * P.ld + P.c0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + c);
+        a[c] = v.x; a[c + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++) a[c] = c < jb ? src[c] : 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < JB; c++) a[c] = 0.0;
+  }
+
+#pragma unroll
+  for (int j = 0; j < JB; j++) {
+    if (j < jb) {   // uniform
+      const long long diag = P.r0 + j;
+      const int par = j & 1;
+      double bv = -1.0;
+      int br = 0x7fffffff;
+      if (myrow >= diag) { bv = fabs(a[j]); br = (int)myrow; }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, br, off);
+        argmax_combine(bv, br, ov, orow);
+      }
+      if (lane == 0) { s_wv[warp] = bv; s_wr[warp] = br; }
+      __syncthreads();
+      double cv = lane < nwarps ? s_wv[lane] : -1.0;
+      int cr = lane < nwarps ? s_wr[lane] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, cv, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, cr, off);
+        argmax_combine(cv, cr, ov, orow);
+      }
+      if (myrow >= 0 && myrow == (long long)cr) {
+#pragma unroll
+        for (int c = 0; c < JB; c++) x_cand[par][c] = a[c];
+      }
+      if (myrow == diag) {
+#pragma unroll
+        for (int c = 0; c < JB; c++) x_top[par][c] = a[c];
+      }
+      if (tid == 0) { x_cval[par] = cv; x_crow[par] = cr; }
+      cluster.sync();                                  // release/acquire across the cluster
+      if (warp == 0) {
+        double wv = -1.0;
+        int wr = 0x7fffffff, wb = 0;
+        for (int c = lane; c < C; c += 32) {
+          const double ov = *cluster.map_shared_rank(&x_cval[par], c);
+          const int orow = *cluster.map_shared_rank(&x_crow[par], c);
+          if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wb = c; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, wv, off);
+          const int orow = __shfl_xor_sync(0xffffffffu, wr, off);
+          const int ob = __shfl_xor_sync(0xffffffffu, wb, off);
+          if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wb = ob; }
+        }
+        const bool none = (wr == 0x7fffffff);
+        if (none) { wr = (int)diag; wv = 0.0; }
+        if (lane < JB) {
+          const double t = cluster.map_shared_rank(&x_top[par][0], 0)[lane];     // diagonal rows live in CTA 0
+          s_trow[lane] = t;
+          s_prow[lane] = none ? t : cluster.map_shared_rank(&x_cand[par][0], wb)[lane];
+        }
+        if (lane == 0) {
+          s_piv = wr;
+          if (b == 0) {
+            P.ipiv[diag] = wr;
+            if (wv == 0.0) atomicCAS(P.info, 0, (int)diag + 1);
+          }
+        }
+      }
+      __syncthreads();
+      const long long piv = s_piv;
+      const double pval = s_prow[j];
+      const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
+      if (myrow == diag) {
+#pragma unroll
+        for (int c = 0; c < JB; c++) a[c] = s_prow[c];
+      } else if (myrow > diag) {
+        if (myrow == piv) {
+#pragma unroll
+          for (int c = 0; c < JB; c++) a[c] = s_trow[c];
+        }
+        if (pval != 0.0) {
+          const double l = a[j] * rinv;
+          a[j] = l;
+#pragma unroll
+          for (int c = j + 1; c < JB; c++) a[c] = fma(-l, s_prow[c], a[c]);
+        }
+      }
+    }
+  }
+  if (valid) {
+    double *dst = P.K + row * P.ld + P.c0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(a[c], a[c + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++)
+        if (c < jb) dst[c] = a[c];
+    }
+  }
+  cluster.sync();   // nobody may exit while a peer can still read its shared memory
+}
+
+// largest cluster size (<= 16) this device can co-schedule for the cluster panel kernel; 0 = unsupported
+static int cluster_panel_max(UpdesLU *h) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  if (cudaFuncSetAttribute(lu_panel_cluster_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+  }
+  for (int c = 16; c >= 1; c >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c); cfg.blockDim = dim3(PANEL_THREADS); cfg.dynamicSmemBytes = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, lu_panel_cluster_kernel<32>, &cfg) == cudaSuccess && nclusters >= 1) {
+      cached = c;
+      break;
+    }
+    cudaGetLastError();
+  }
+  (void)h;
+  return cached;
+}
+
+static int launch_panel_cluster(UpdesLU *h, PanelParams &P, int ctas, int threads, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  prof_begin(PROF_PANEL, (double)(P.n - P.r0) * P.jb * P.jb, st);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<32>, P);
+  prof_end(st);
+  if (e != cudaSuccess) return (int)e;
+  ++g_launch_count;
+  (void)h;
+  return 0;
+}
+
 template <int JB, int RPT>
 static int launch_panel(UpdesLU *h, PanelParams &P, int threads, cudaStream_t st) {
   void *args[] = {&P};
@@ -247,6 +434,22 @@ int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ip
   const int JBmax = panel_width_for(h, m);
   if (JBmax == 0) return -3;
   if (jb > JBmax) return -4;
+  // short panels: one thread-block cluster, DSMEM exchange, hardware cluster barrier
+  if (h->panel_variant == 1 && JBmax == 32) {
+    const int cmax = cluster_panel_max(h);
+    if (cmax > 0 && m <= (int64_t)cmax * PANEL_THREADS) {
+      int c = 1;
+      while ((int64_t)c * PANEL_THREADS < m) c <<= 1;
+      int64_t Rc = (m + c - 1) / c;
+      Rc = (Rc + 31) / 32 * 32;
+      if (Rc < 32) Rc = 32;
+      PanelParams Pc;
+      Pc.K = V.ptr; Pc.ld = V.ld; Pc.n = V.rows; Pc.r0 = r0; Pc.c0 = c0; Pc.jb = jb; Pc.rows_per_cta = (int)Rc;
+      Pc.ipiv = ipiv; Pc.info = info; Pc.cand = nullptr; Pc.top = nullptr; Pc.candval = nullptr; Pc.candrow = nullptr;
+      Pc.barrier = nullptr; Pc.barrier_base = 0; Pc.num_ctas = c;
+      return launch_panel_cluster(h, Pc, c, (int)Rc, st);
+    }
+  }
   const int rpt = 32 / JBmax;
   // rows per CTA: enough CTAs to fill the machine, at least 64 rows each, a multiple of 32
   int ctas = (int)((m + 63) / 64);

@@ -51,6 +51,9 @@ class LUFactorization:
         _lib.check(rc, "updes_lu_solve")
         return B
 
+    def set_panel_variant(self, variant: int):
+        _lib.check(self._lib.updes_lu_set_panel_variant(self._handle, variant), "updes_lu_set_panel_variant")
+
     def set_solve_variant(self, variant: int):
         _lib.check(self._lib.updes_lu_set_solve_variant(self._handle, variant), "updes_lu_set_solve_variant")
 
