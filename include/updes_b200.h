@@ -134,7 +134,8 @@ int updes_lu_panel(UpdesLU *handle, double *K, int64_t r0, int64_t nc, int32_t *
 int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t ld);
 /* cap the persistent GEMM grid (0 = one CTA per SM) so NCCL kernels can run beside the update */
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
-/* trailing-update GEMM schedule: 0 = one 128x128 CTA per SM, 1 = ping-pong (two 128x64 CTAs per SM) */
+/* trailing-update GEMM schedule, bit 0: 1 = ping-pong (two 128x64 CTAs per SM), 0 = one 128x128 CTA per SM;
+ * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
 /* base panels: 1 = panels of <= 10 240 rows run in one thread-block cluster (DSMEM exchange, hardware
  * cluster barrier; default), 0 = always the grid-wide cooperative kernel */

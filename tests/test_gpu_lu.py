@@ -18,9 +18,9 @@ def _matrix(n, seed=0, ld=None, dominant=False):
     return A, K.cuda()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 128, 64), (300, 200, 32), (1000, 96, 128), (77, 500, 48),
-                                   (2048, 2048, 512), (129, 33, 16), (64, 32, 32), (4000, 64, 256), (5000, 3001, 96)])
+                                   (2048, 2048, 512), (129, 33, 16), (64, 32, 32), (4000, 64, 256), (5000, 3001, 96), (6000, 2500, 512)])
 def test_dgemm_sub(m, n, k, variant):
     """C -= A @ B on sub-blocks of one matrix vs torch (DMMA + TMA kernel, all tile shapes / edges)."""
     import torch

@@ -88,7 +88,8 @@ __device__ __forceinline__ void tile_coords(long long t, int tiles_m, int tiles_
 // NW = 4: "ping-pong" -- two independent 4-warp CTAs per SM, each with a 128 x 64 tile and the same
 //         64 x 32 per-warp accumulator block: while one CTA runs its epilogue (the exposed C
 //         read-modify-write) the other keeps the FP64 tensor pipe busy.
-template <int BN, int NW>
+// KSUB = 16-deep k sub-tiles per pipeline stage: 2 halves the number of barrier rounds per flop.
+template <int BN, int NW, int KSUB>
 struct GemmCfg {
   static constexpr int THREADS = NW * 32;
   static constexpr int MIN_CTAS = NW == 4 ? 2 : 1;
@@ -98,15 +99,16 @@ struct GemmCfg {
   static constexpr int MI = WM / 8;                // 8-row fragments per warp
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 8;
   static constexpr int B_BYTES = BN * GEMM_BK * 8;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = NW == 4 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
+  static constexpr int STAGES = (NW == 4 ? 4 : (BN == 128 ? 6 : 8)) / KSUB;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int NW>
+template <int BN, int NW, int KSUB>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 ? 2 : 1))
 dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmParams P) {
-  using Cfg = GemmCfg<BN, NW>;
+  using Cfg = GemmCfg<BN, NW, KSUB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
@@ -124,7 +126,7 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int tiles_m = (int)((P.m + GEMM_BM - 1) / GEMM_BM);
   const int tiles_n = (int)((P.n + BN - 1) / BN);
   const long long ntiles = (long long)tiles_m * tiles_n;
-  const int ktiles = (int)(P.k / GEMM_BK);
+  const int ktiles = (int)(P.k / (GEMM_BK * KSUB));
 
   // ------------------------------ producer state (thread 0) ------------------------------
   // No dedicated producer warp: a 9th warp would round the CTA up to 12 warps of register
@@ -163,11 +165,15 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int arow = (int)(P.ra + (long long)mt * GEMM_BM);
     const int bcol = (int)(P.cb + (long long)nt * BN);
     mbar_expect_tx(full, Cfg::STAGE_BYTES);
-    const uint32_t sa = smem_base + p_stage * Cfg::STAGE_BYTES;
-    tma_load_2d(sa, &mapA, (int)(P.ca + p_kt * GEMM_BK), arow, full);
 #pragma unroll
-    for (int g = 0; g < BN / 16; g++)
-      tma_load_2d(sa + Cfg::A_BYTES + g * 2048, &mapB, bcol + 16 * g, (int)(P.rb + p_kt * GEMM_BK), full);
+    for (int ks = 0; ks < KSUB; ks++) {
+      const uint32_t sa = smem_base + p_stage * Cfg::STAGE_BYTES + ks * Cfg::SUB_BYTES;
+      const int kk = (p_kt * KSUB + ks) * GEMM_BK;
+      tma_load_2d(sa, &mapA, (int)(P.ca + kk), arow, full);
+#pragma unroll
+      for (int g = 0; g < BN / 16; g++)
+        tma_load_2d(sa + Cfg::A_BYTES + g * 2048, &mapB, bcol + 16 * g, (int)(P.rb + kk), full);
+    }
     if (++p_stage == Cfg::STAGES) { p_stage = 0; p_phase ^= 1; }
     if (++p_kt == ktiles) p_kt = 0;
   };
@@ -219,8 +225,10 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (threadIdx.x == 0) produce_one();
         mbar_wait(bars + 8 * stage, phase);
       }
-      const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES + a_row_off;
-      const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < KSUB; ks++) {
+      const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES + ks * Cfg::SUB_BYTES + a_row_off;
+      const uint32_t sb = smem_base + stage * Cfg::STAGE_BYTES + ks * Cfg::SUB_BYTES + Cfg::A_BYTES;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         double b_ev[4], b_od[4];
@@ -241,6 +249,7 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             dmma(acc[i][jn][0], acc[i][jn][1], a_od, b_od[jn]);
           }
         }
+      }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * (Cfg::STAGES + stage));
@@ -327,12 +336,12 @@ int lu_bind_view(UpdesLU *h, int slot, const double *ptr, int64_t rows, int64_t 
   return 0;
 }
 
-template <int BN, int NW>
+template <int BN, int NW, int KSUB>
 static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const GemmParams &P, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, NW>;
+  using Cfg = GemmCfg<BN, NW, KSUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    UPDES_CUDA_TRY(cudaFuncSetAttribute(dgemm_sub_kernel<BN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(dgemm_sub_kernel<BN, NW, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -344,7 +353,7 @@ static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const G
   Q.next_counter = h->gemm_counters + ((h->gemm_launch_id + 1) % UPDES_GEMM_COUNTERS);
   h->gemm_launch_id++;
   prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
-  dgemm_sub_kernel<BN, NW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, Q);
+  dgemm_sub_kernel<BN, NW, KSUB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, Q);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;
@@ -359,12 +368,15 @@ int dgemm_sub(UpdesLU *h, int va, int64_t ra, int64_t ca, int vb, int64_t rb, in
   if (!VA.ptr || !VB.ptr || !VC.ptr) return -2;
   GemmParams P;
   P.C = VC.ptr; P.ld = VC.ld; P.rc = rc; P.cc = cc; P.ra = ra; P.ca = ca; P.rb = rb; P.cb = cb; P.m = m; P.n = n; P.k = k;
-  if (n <= 32) return launch_gemm<32, 8>(h, VA, VB, P, st);
-  if (n <= 64) return launch_gemm<64, 8>(h, VA, VB, P, st);
-  // wide updates: ping-pong (two 128x64 CTAs per SM) once there are enough tiles to fill every slot
+  if (n <= 32) return launch_gemm<32, 8, 1>(h, VA, VB, P, st);
+  if (n <= 64) return launch_gemm<64, 8, 1>(h, VA, VB, P, st);
+  // wide updates: ping-pong (two 128x64 CTAs per SM) once there are enough tiles to fill every slot;
+  // 32-deep pipeline stages (KSUB = 2) when k allows and gemm_kdeep is set
   const long long tiles64 = ((m + GEMM_BM - 1) / GEMM_BM) * ((n + 63) / 64);
-  if (h->gemm_variant == 1 && tiles64 >= 2LL * h->num_sms) return launch_gemm<64, 4>(h, VA, VB, P, st);
-  return launch_gemm<128, 8>(h, VA, VB, P, st);
+  const bool deep = h->gemm_kdeep && (k % (2 * GEMM_BK) == 0) && k >= 128;
+  if (h->gemm_variant == 1 && tiles64 >= 2LL * h->num_sms)
+    return deep ? launch_gemm<64, 4, 2>(h, VA, VB, P, st) : launch_gemm<64, 4, 1>(h, VA, VB, P, st);
+  return deep ? launch_gemm<128, 8, 2>(h, VA, VB, P, st) : launch_gemm<128, 8, 1>(h, VA, VB, P, st);
 }
 
 }  // namespace updes
@@ -396,8 +408,9 @@ extern "C" int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas) {
 
 extern "C" int updes_lu_set_gemm_variant(UpdesLU *handle, int variant) {
   if (!handle) return -1;
-  if (variant < 0 || variant > 1) return -2;
-  handle->gemm_variant = variant;
+  if (variant < 0 || variant > 3) return -2;
+  handle->gemm_variant = variant & 1;      // bit 0: ping-pong schedule
+  handle->gemm_kdeep = (variant >> 1) & 1; // bit 1: 32-deep pipeline stages
   return 0;
 }
 

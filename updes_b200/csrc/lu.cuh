@@ -23,6 +23,7 @@ struct UpdesLU {
   int gemm_ctas = 0;       // 0 = one CTA per SM; smaller leaves SMs free for concurrent NCCL kernels
   int64_t panel_cap = 0;   // rows a 32-wide register-resident panel can hold (0 = num_sms * 640); test hook
   int panel_variant = 1;   // 1: short panels (<= 10 240 rows) use the thread-block-cluster kernel; 0: always the grid kernel
+  int gemm_kdeep = 1;      // 1 (default): 32-deep pipeline stages (two 16-k sub-tiles per barrier round) when k % 32 == 0
   int gemm_variant = 1;    // 1 (default): ping-pong, two 128x64 CTAs per SM; 0: one 128x128 CTA per SM
   MatView view[UPDES_MAX_VIEWS];
   // device workspace of the panel kernel
