@@ -84,8 +84,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
 
   unsigned int target = P.barrier_base;
 
+  // The column loop is unrolled 8 steps at a time and the register row is rotated left by 8 between
+  // groups, so the current column is always one of registers 0..7 (static indexing) while the kernel
+  // body stays ~4x smaller than a full 32-step unroll (ncu: instruction-cache misses were the second
+  // largest stall).  Every thread applies the same rotation, so published rows are exchanged in
+  // rotated form; after JB/8 groups the rotation is the identity again.
+#pragma unroll 1
+  for (int g = 0; g < JB / 8; g++) {
+  const int live = JB - 8 * g;                 // registers [0, live) hold columns not yet eliminated
 #pragma unroll
-  for (int j = 0; j < JB; j++) {
+  for (int jl = 0; jl < 8; jl++) {
+    const int j = 8 * g + jl;
     if (j < jb) {   // uniform
       const long long diag = P.r0 + j;
       const int par = j & 1;
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
       int br = 0x7fffffff;
 #pragma unroll
       for (int q = 0; q < RPT; q++)
-        if (myrow[q] >= diag) argmax_combine(bv, br, fabs(a[q][j]), (int)myrow[q]);
+        if (myrow[q] >= diag) argmax_combine(bv, br, fabs(a[q][jl]), (int)myrow[q]);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
       __syncthreads();
       // ---- 4. interchange + rank-1 update ------------------------------------------------------------
       const long long piv = s_piv;
-      const double pval = s_prow[j];
+      const double pval = s_prow[jl];
       const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
 #pragma unroll
       for (int q = 0; q < RPT; q++) {
@@ -192,13 +201,26 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
           for (int c = 0; c < JB; c++) a[q][c] = s_trow[c];
         }
         if (pval != 0.0) {
-          const double l = a[q][j] * rinv;
-          a[q][j] = l;
+          const double l = a[q][jl] * rinv;
+          a[q][jl] = l;
 #pragma unroll
-          for (int c = j + 1; c < JB; c++) a[q][c] = fma(-l, s_prow[c], a[q][c]);
+          for (int c = jl + 1; c < JB; c++)
+            if (c < live) a[q][c] = fma(-l, s_prow[c], a[q][c]);
         }
       }
     }
+  }
+  // rotate the register rows left by 8 columns
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    double t8[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) t8[c] = a[q][c];
+#pragma unroll
+    for (int c = 0; c < JB - 8; c++) a[q][c] = a[q][c + 8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[q][JB - 8 + c] = t8[c];
+  }
   }
 
   // ---- store ---------------------------------------------------------------------------
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cluster variant for short panels (m <= 16 x 640 rows): the CTAs of ONE thread-block cluster hold the
+// Cluster variant for short panels (m <= 16 x 512 rows): the CTAs of ONE thread-block cluster hold the
 // panel, candidates are exchanged through distributed shared memory and the per-column barrier is a
 // hardware cluster barrier (~0.6 us per column instead of ~5 us through global memory).  Same
 // algorithm and tie-breaking as lu_panel_kernel; two candidate buffers alternate by column parity, so
@@ -227,8 +249,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_kernel(PanelParams 
 // ------------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 
+constexpr int CLUSTER_PANEL_THREADS = 512;   // 128 registers per thread: no spills with the DSMEM pointers live
+
 template <int JB>
-__global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_cluster_kernel(PanelParams P) {
+__global__ void __launch_bounds__(CLUSTER_PANEL_THREADS, 1) lu_panel_cluster_kernel(PanelParams P) {
   __shared__ double s_wv[32];
   __shared__ int s_wr[32];
   __shared__ double s_prow[JB], s_trow[JB];
@@ -263,14 +287,18 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_cluster_kernel(Pane
     for (int c = 0; c < JB; c++) a[c] = 0.0;
   }
 
+#pragma unroll 1
+  for (int g = 0; g < JB / 8; g++) {           // 8 unrolled column steps per group, rows rotated by 8 in between
+  const int live = JB - 8 * g;
 #pragma unroll
-  for (int j = 0; j < JB; j++) {
+  for (int jl = 0; jl < 8; jl++) {
+    const int j = 8 * g + jl;
     if (j < jb) {   // uniform
       const long long diag = P.r0 + j;
       const int par = j & 1;
       double bv = -1.0;
       int br = 0x7fffffff;
-      if (myrow >= diag) { bv = fabs(a[j]); br = (int)myrow; }
+      if (myrow >= diag) { bv = fabs(a[jl]); br = (int)myrow; }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -329,7 +357,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_cluster_kernel(Pane
       }
       __syncthreads();
       const long long piv = s_piv;
-      const double pval = s_prow[j];
+      const double pval = s_prow[jl];
       const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
       if (myrow == diag) {
 #pragma unroll
@@ -340,13 +368,24 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel_cluster_kernel(Pane
           for (int c = 0; c < JB; c++) a[c] = s_trow[c];
         }
         if (pval != 0.0) {
-          const double l = a[j] * rinv;
-          a[j] = l;
+          const double l = a[jl] * rinv;
+          a[jl] = l;
 #pragma unroll
-          for (int c = j + 1; c < JB; c++) a[c] = fma(-l, s_prow[c], a[c]);
+          for (int c = jl + 1; c < JB; c++)
+            if (c < live) a[c] = fma(-l, s_prow[c], a[c]);
         }
       }
     }
+  }
+  {
+    double t8[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) t8[c] = a[c];
+#pragma unroll
+    for (int c = 0; c < JB - 8; c++) a[c] = a[c + 8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[JB - 8 + c] = t8[c];
+  }
   }
   if (valid) {
     double *dst = P.K + row * P.ld + P.c0;
@@ -372,7 +411,7 @@ static int cluster_panel_max(UpdesLU *h) {
   }
   for (int c = 16; c >= 1; c >>= 1) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(c); cfg.blockDim = dim3(PANEL_THREADS); cfg.dynamicSmemBytes = 0;
+    cfg.gridDim = dim3(c); cfg.blockDim = dim3(CLUSTER_PANEL_THREADS); cfg.dynamicSmemBytes = 0;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -437,9 +476,9 @@ int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ip
   // short panels: one thread-block cluster, DSMEM exchange, hardware cluster barrier
   if (h->panel_variant == 1 && JBmax == 32) {
     const int cmax = cluster_panel_max(h);
-    if (cmax > 0 && m <= (int64_t)cmax * PANEL_THREADS) {
+    if (cmax > 0 && m <= (int64_t)cmax * CLUSTER_PANEL_THREADS) {
       int c = 1;
-      while ((int64_t)c * PANEL_THREADS < m) c <<= 1;
+      while ((int64_t)c * CLUSTER_PANEL_THREADS < m) c <<= 1;
       int64_t Rc = (m + c - 1) / c;
       Rc = (Rc + 31) / 32 * 32;
       if (Rc < 32) Rc = 32;
