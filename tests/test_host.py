@@ -229,3 +229,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation comes before any CUDA call: negative status = index of the offending argument."""
+    import ctypes
+    from updes_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.updes_lu_create(ctypes.byref(h), 100, 7) == -3            # ld not a multiple of 16
+    assert lib.updes_lu_create(ctypes.byref(h), 0, 16) == -2             # n <= 0
+    assert lib.updes_lu_create(None, 10, 16) == -1
+    assert lib.updes_lu_factor(None, None, None, None, None) == -1
+    assert lib.updes_lu_solve(None, None, None, None, 0, 1, 0, None) == -1
+    rows = _lib.UpdesRows()
+    assert lib.updes_assemble_rows(0, 1.0, 0, 3, None, ctypes.byref(rows), 0, 1, 7, None, 16, None) == -3   # N <= 0
+    assert lib.updes_assemble_rows(0, 1.0, 10, 99, None, ctypes.byref(rows), 0, 1, 7, None, 16, None) == -4  # M > 15
+    assert lib.updes_assemble_rows(0, 1.0, 10, 3, None, ctypes.byref(rows), 0, 1, 7, None, 16, None) == -5   # no centres
+    assert lib.updes_eval_jets(0, 1.0, 0, 3, None, None, 0, 1, None, 1, None, None, None, None, None) == -3
+    assert lib.updes_lu_set_gemm_variant(None, 0) == -1
