@@ -48,7 +48,7 @@ def _worker(rank, world, port, n, nb, seed, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,nb", [(2, 200, 32), (2, 257, 64), (3, 330, 32), (2, 96, 32)])
+@pytest.mark.parametrize("world,n,nb", [(2, 200, 32), (2, 257, 64), (3, 330, 32), (2, 96, 32), (4, 301, 32), (2, 67, 64)])
 def test_block_cyclic_lu_matches_lapack(tmp_path, world, n, nb):
     import scipy.linalg as sla
     out = str(tmp_path / "res.npz")

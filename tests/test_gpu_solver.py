@@ -124,3 +124,41 @@ def test_reference_test_operators_on_its_own_mesh_gpu():
     grads = u.gradient_vec(cloud.sorted_nodes, sol.coeffs, cloud.sorted_nodes, rbf)
     divs = u.divergence_vec(cloud.sorted_nodes, np.stack([sol.coeffs, sol.coeffs], -1), cloud.sorted_nodes, rbf)
     assert np.allclose(np.linalg.norm(grads, axis=-1), 0, atol=1e-2) and np.allclose(divs, 0, atol=1e-2)
+
+
+def test_differentiable_solve_wrt_boundary_data():
+    """d(loss)/d(boundary array) through the factored system: K^-T via the transposed solve, checked
+    against central finite differences (the DP demos' use case, demos/Laplace/10_...:90-104)."""
+    import torch
+    from updes_b200 import assembly as asm
+    from updes_b200.autodiff import linear_solve
+    from updes_b200.linalg import LUFactorization
+    cloud = u.SquareCloud(Nx=14, Ny=12, facet_types=CONFIG1_FACETS, noise_key=4)
+    M, n = 3, cloud.N + 3
+    coef = np.tile([0.0, 0, 0, 1.0, 1.0], (cloud.Ni, 1))
+    rows = asm.DeviceRows(cloud, asm.build_operator_rows(cloud, coef))
+    K = asm.assemble_system(rows, "polyharmonic", 1.0, M)
+    Kd = K[:, :n].clone()
+    lu = LUFactorization(K, n).factor()
+    north = torch.as_tensor(np.asarray(cloud.facet_nodes["North"])).cuda()
+    w = torch.linspace(0.5, 1.5, n, dtype=torch.float64, device="cuda")
+
+    def loss_of(bc):
+        b = torch.zeros(n, dtype=torch.float64, device="cuda").index_put((north,), bc)
+        c = linear_solve(lu, b)
+        return (w * c * c).sum()
+
+    bc = torch.sin(torch.linspace(0, 3.0, len(north), dtype=torch.float64, device="cuda")).requires_grad_(True)
+    loss = loss_of(bc)
+    loss.backward()
+    g = bc.grad.clone()
+    # reference gradient with dense algebra: dL/db = K^-T (2 w c), restricted to the North rows
+    b = torch.zeros(n, dtype=torch.float64, device="cuda").index_put((north,), bc.detach())
+    c = torch.linalg.solve(Kd, b)
+    gref = torch.linalg.solve(Kd.T, 2 * w * c)[north]
+    assert float((g - gref).abs().max() / gref.abs().max()) <= 1e-8
+    # and one finite-difference probe
+    e = torch.zeros_like(bc); e[3] = 1.0
+    h = 1e-6
+    fd = (loss_of(bc.detach() + h * e) - loss_of(bc.detach() - h * e)) / (2 * h)
+    assert abs(float(fd) - float(g[3])) <= 1e-5 * max(1.0, abs(float(g[3])))

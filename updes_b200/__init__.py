@@ -15,4 +15,6 @@ from .operators import (BatchPoints, OperatorLoweringError, SteadySol, boundary_
                         nodal_value, pde_multi_solver, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
                         zerofy_periodic_cond)
 
+from .autodiff import linear_solve
+
 __version__ = "0.1.0"
