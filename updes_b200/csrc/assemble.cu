@@ -5,10 +5,10 @@
 //        [  P^T     0   ]]     rows N..N+M-1    polynomial constraints   assembly.py:39-59,:80-83
 //
 // Every entry is an independent closed form, so the kernel is a pure HBM-write stream:
-// algorithmic bytes = 8 per entry.  One CTA owns a TR x 512 tile: each thread keeps
-// the coordinates of its two adjacent centres in registers, row descriptors (evaluation point,
+// algorithmic bytes = 8 per entry.  One CTA owns a TR x 512 or 1024 tile: each thread keeps
+// the coordinates of its two or four adjacent centres in registers, row descriptors (evaluation point,
 // pre-combined coefficients, optional periodic partner) are staged in shared memory once per
-// tile, and every row is written with 16-byte streaming stores (one warp = 512 contiguous bytes).
+// tile, and every row is written with 16-byte streaming stores (one warp = 512 B or 1 KB contiguous).
 #include "common.cuh"
 
 namespace updes {
@@ -16,7 +16,8 @@ namespace updes {
 long long g_launch_count = 0;
 
 constexpr int ASM_THREADS = 256;
-constexpr int ASM_TC = ASM_THREADS * 2;  // columns per tile
+// adjacent columns per thread: 2 for the closed-form Laplacian rows (HBM-bound: 12.5 ms vs 14.2 ms with 4 at
+// n = 90 003), 4 for general jets (FP64/LSU-bound: fewer row-descriptor loads per entry, 18.3 ms vs 20.5 ms)
 constexpr int ASM_TR = 32;               // rows per tile
 
 struct RowStage {
@@ -43,8 +44,9 @@ __device__ __forceinline__ void load_point(RowPoint &rp, const double *pts, int 
   rp.c34 = c[3] + c[4];
 }
 
-template <int KIND, int MASK>
+template <int KIND, int MASK, int ASM_CPT>
 __global__ void __launch_bounds__(ASM_THREADS) assemble_phi_kernel(AsmParams P) {
+  constexpr int ASM_TC = ASM_THREADS * ASM_CPT;   // columns per tile
   __shared__ RowStage stage[ASM_TR];
   const long long r_tile = P.row0 + (long long)blockIdx.y * ASM_TR;
   const int nr = (int)min((long long)ASM_TR, P.row0 + P.nrows - r_tile);
@@ -59,32 +61,45 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_phi_kernel(AsmParams P) 
     st.skip = P.rows.skip ? P.rows.skip[r] : -1;
     stage[threadIdx.x] = st;
   }
-  const long long j = P.col0 + (long long)blockIdx.x * ASM_TC + 2 * threadIdx.x;
+  const long long j = P.col0 + (long long)blockIdx.x * ASM_TC + ASM_CPT * threadIdx.x;
   const long long jend = P.col0 + P.ncols;
-  double cx0 = 0, cy0 = 0, cx1 = 0, cy1 = 0;
-  if (j + 1 < jend) {
-    const double4 c = *reinterpret_cast<const double4 *>(P.centres + 2 * j);  // 32-byte aligned: j even
-    cx0 = c.x; cy0 = c.y; cx1 = c.z; cy1 = c.w;
-  } else if (j < jend) {
-    cx0 = P.centres[2 * j]; cy0 = P.centres[2 * j + 1];
+  double cx[ASM_CPT], cy[ASM_CPT];
+#pragma unroll
+  for (int u = 0; u < ASM_CPT; u += 2) {
+    cx[u] = cy[u] = cx[u + 1] = cy[u + 1] = 0.0;
+    if (j + u + 1 < jend) {
+      const double4 c = *reinterpret_cast<const double4 *>(P.centres + 2 * (j + u));  // 32-byte aligned: j even
+      cx[u] = c.x; cy[u] = c.y; cx[u + 1] = c.z; cy[u + 1] = c.w;
+    } else if (j + u < jend) {
+      cx[u] = P.centres[2 * (j + u)]; cy[u] = P.centres[2 * (j + u) + 1];
+    }
   }
   __syncthreads();
   if (j >= jend) return;
   double *o = P.out + (r_tile - P.row0) * P.ld + (j - P.col0);
-  const bool pair = (j + 1 < jend);
+  const int ncol = (int)min((long long)ASM_CPT, jend - j);
 #pragma unroll 2
   for (int t = 0; t < nr; t++) {
     const RowStage &st = stage[t];
-    double v0 = entry_one_point<KIND, MASK>(st.a, cx0, cy0, P.ip, P.e2);
-    double v1 = entry_one_point<KIND, MASK>(st.a, cx1, cy1, P.ip, P.e2);
+    double v[ASM_CPT];
+#pragma unroll
+    for (int u = 0; u < ASM_CPT; u++) v[u] = entry_one_point<KIND, MASK>(st.a, cx[u], cy[u], P.ip, P.e2);
     if (st.has_b) {
-      v0 += entry_one_point<KIND, MASK>(st.b, cx0, cy0, P.ip, P.e2);
-      v1 += entry_one_point<KIND, MASK>(st.b, cx1, cy1, P.ip, P.e2);
+#pragma unroll
+      for (int u = 0; u < ASM_CPT; u++) v[u] += entry_one_point<KIND, MASK>(st.b, cx[u], cy[u], P.ip, P.e2);
     }
-    if (st.skip == (int)j) v0 = 0.0;
-    if (st.skip == (int)j + 1) v1 = 0.0;
-    if (pair) __stcs(reinterpret_cast<double2 *>(o), make_double2(v0, v1));
-    else __stcs(o, v0);
+    const int sk = st.skip - (int)j;                 // skipped column relative to this thread's first column
+#pragma unroll
+    for (int u = 0; u < ASM_CPT; u++)
+      if (sk == u) v[u] = 0.0;
+    if (ncol == ASM_CPT) {
+#pragma unroll
+      for (int u = 0; u < ASM_CPT; u += 2) __stcs(reinterpret_cast<double2 *>(o + u), make_double2(v[u], v[u + 1]));
+    } else {
+#pragma unroll
+      for (int u = 0; u < ASM_CPT; u++)
+        if (u < ncol) __stcs(o + u, v[u]);
+    }
     o += P.ld;
   }
 }
@@ -148,19 +163,21 @@ __global__ void assemble_pt_rows_kernel(PtParams P) {
 
 template <int KIND>
 static int launch_phi(int mask, const AsmParams &P, cudaStream_t st) {
-  dim3 grid((unsigned)((P.ncols + ASM_TC - 1) / ASM_TC), (unsigned)((P.nrows + ASM_TR - 1) / ASM_TR));
+  const unsigned gy = (unsigned)((P.nrows + ASM_TR - 1) / ASM_TR);
   if (mask & JET_ISO) {
-    if (mask & JET_VAL) assemble_phi_kernel<KIND, JET_ISO | JET_VAL><<<grid, ASM_THREADS, 0, st>>>(P);
-    else assemble_phi_kernel<KIND, JET_ISO><<<grid, ASM_THREADS, 0, st>>>(P);
+    dim3 grid((unsigned)((P.ncols + ASM_THREADS * 2 - 1) / (ASM_THREADS * 2)), gy);
+    if (mask & JET_VAL) assemble_phi_kernel<KIND, JET_ISO | JET_VAL, 2><<<grid, ASM_THREADS, 0, st>>>(P);
+    else assemble_phi_kernel<KIND, JET_ISO, 2><<<grid, ASM_THREADS, 0, st>>>(P);
     UPDES_LAUNCH_CHECK();
     return 0;
   }
+  dim3 grid((unsigned)((P.ncols + ASM_THREADS * 4 - 1) / (ASM_THREADS * 4)), gy);
   switch (mask & 7) {
-    case 1: assemble_phi_kernel<KIND, 1><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 2: assemble_phi_kernel<KIND, 2><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 3: assemble_phi_kernel<KIND, 3><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 6: assemble_phi_kernel<KIND, 6><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    default: assemble_phi_kernel<KIND, 7><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    case 1: assemble_phi_kernel<KIND, 1, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    case 2: assemble_phi_kernel<KIND, 2, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    case 3: assemble_phi_kernel<KIND, 3, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    case 6: assemble_phi_kernel<KIND, 6, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    default: assemble_phi_kernel<KIND, 7, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
   }
   UPDES_LAUNCH_CHECK();
   return 0;
