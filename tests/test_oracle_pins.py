@@ -156,3 +156,17 @@ def test_golden_fixture_matches_oracle(oracle):
     K = oracle.assemble_K(cloud, "polyharmonic", 1, 3, coef)
     assert np.array_equal(cloud.sorted_nodes, g["sorted_nodes"])
     assert np.max(np.abs(K[g["rows"]][:, g["cols"]] - g["K_sample"])) <= 1e-13 * np.max(np.abs(g["K_sample"]))
+
+
+def test_golden_solution_vectors_match_reference_formulation(oracle):
+    """The committed q / vals / coeffs of config 1 are what the reference formulation (inv + GEMM + QR)
+    yields today, and they solve the reformulated system K c = [q; 0], vals = [Phi P] c."""
+    g = np.load(os.path.join(GOLDEN, "config1_30x20_phs3.npz"))
+    cloud = oracle.RefSquareCloud(30, 20, CONFIG1_FACETS)
+    coef = np.tile([0.0, 0, 0, 1.0, 1.0], (cloud.Ni, 1))
+    vals, coeffs, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 1, coef, g["q"])
+    assert np.max(np.abs(vals - g["vals"])) <= 1e-9 * np.max(np.abs(g["vals"]))
+    K = oracle.assemble_K(cloud, "polyharmonic", 1, 3, coef)
+    c = np.linalg.solve(K, np.concatenate([g["q"], np.zeros(3)]))
+    A = oracle.assemble_A(cloud, "polyharmonic", 1, 3)
+    assert np.max(np.abs(A[:cloud.N] @ c - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))
