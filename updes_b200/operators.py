@@ -397,6 +397,7 @@ class _System:
 
     def __init__(self, cloud, kind, param, M, table):
         self.kind, self.param, self.M = kind, param, M
+        self.cloud = cloud                   # the cache key uses id(cloud): keep it alive while cached
         self.rows = _asm.DeviceRows(cloud, table)
         self.K = _asm.assemble_system(self.rows, kind, param, M)
         self.n = cloud.N + M
@@ -444,6 +445,7 @@ class _DistSystem:
     def __init__(self, cloud, kind, param, M, table, world, rank):
         from .distributed import ColumnBlockCyclic, CudaBackend, DistributedLU
         self.kind, self.param, self.M = kind, param, M
+        self.cloud = cloud                   # the cache key uses id(cloud): keep it alive while cached
         self.rows = _asm.DeviceRows(cloud, table)
         self.n = cloud.N + M
         self.layout = ColumnBlockCyclic(self.n, default_block_width(self.n, world), world)
@@ -580,6 +582,11 @@ def _reference_mat(cloud, kind, param, M, system):
     A is symmetric, so B[r, :] = (inv(A) diffMat[r, :]^T)[:N]: N right-hand sides against the LU of A."""
     torch = system.rows.torch
     N = cloud.N
+    if N > 20000:
+        raise MemoryError("SteadySol.mat (the reference's B = diffMat inv(A)[:, :N]) needs N = %d right-hand sides "
+                          "against inv(A) and a second N x N matrix; it is only provided for N <= 20000" % N)
+    if isinstance(system, _DistSystem):
+        raise NotImplementedError("SteadySol.mat is not available on the multi-GPU path")
     D = _asm.assemble_system(system.rows, kind, param, M)[:N].contiguous()     # fresh copy: K holds LU now
     X = _interp_system(cloud, kind, param, M).lu.solve(D)
     return X[:, :N].cpu().numpy()
