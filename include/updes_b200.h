@@ -113,6 +113,23 @@ int updes_lu_destroy(UpdesLU *handle);
 /* Factor K in place (row-major, partial pivoting by rows).  ipiv[n] (device, int32, 0-based:
  * row k was exchanged with row ipiv[k]); info (device int32): 0 or 1-based first zero pivot. */
 int updes_lu_factor(UpdesLU *handle, double *K, int32_t *ipiv, int32_t *info, void *stream);
+/* Same with row equilibration first (`scale` vector): every row is multiplied by the power of two
+ * that brings its largest magnitude into [1, 2) -- exact, so the factors are those of diag(scale) K -- and the
+ * factors are written to scale[n] (device, caller-owned; it must stay alive as long as the handle solves:
+ * updes_lu_solve multiplies right-hand sides by it).  Collocation rows differ in scale by orders of magnitude
+ * (operator rows ~ 1/DT or 9 r, boundary rows ~ r^3, polynomial rows ~ 1), which is what partial pivoting
+ * compares across. */
+int updes_lu_factor_scaled(UpdesLU *handle, double *K, int32_t *ipiv, double *scale, int32_t *info, void *stream);
+/* Building blocks of the same for column-sharded matrices (row maxima are combined across ranks by the caller):
+ * out[r] = max_c |A[r][c]| over c < cols;  scale[i] = 2^-floor(log2 absmax[i]) (1 for zero rows);
+ * A[r][:] *= scale[r];  updes_lu_set_row_scale tells the handle which factors its solves apply (NULL = none). */
+int updes_row_absmax(const double *A, int64_t rows, int64_t cols, int64_t ld, double *out, void *stream);
+int updes_scale_from_absmax(const double *absmax, int64_t n, double *scale, void *stream);
+int updes_row_scale(double *A, int64_t rows, int64_t cols, int64_t ld, const double *scale, void *stream);
+int updes_lu_set_row_scale(UpdesLU *handle, const double *scale);
+/* Internal-failure flags of the handle's kernels (synchronises `stream`): bit 0 = a wait inside a triangular
+ * sweep timed out.  A timed-out grid barrier of the panel kernel is reported through info = -1. */
+int updes_lu_status(UpdesLU *handle, int32_t *host_flags, void *stream);
 /* Solve K X = B for nrhs right-hand sides using the factors.  B is [nrhs][ldb] (each
  * right-hand side contiguous, ldb >= n), overwritten by X.  transpose != 0 solves K^T X = B (adjoint
  * solves; same factors: U^T w = b, L^T z = w, x = P^T z).  Use the handle that factored. */
@@ -137,10 +154,13 @@ int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule, bit 0: 1 = ping-pong (two 128x64 CTAs per SM), 0 = one 128x128 CTA per SM;
  * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
-/* base panels: 1 = panels of <= 10 240 rows run in one thread-block cluster (DSMEM exchange, hardware
- * cluster barrier; default), 0 = always the grid-wide cooperative kernel */
+/* base panels: 2 (default) = implicit-pivoting kernels -- panels of <= 8 192 rows run in one thread-block cluster
+ * whose CTAs push their candidates into each other's shared memory (one split cluster barrier per column), taller
+ * ones in the grid-wide cooperative kernel; 1 = first-generation cluster + grid kernels; 0 = first-generation grid
+ * kernel only */
 int updes_lu_set_panel_variant(UpdesLU *handle, int variant);
-/* triangular solves: 1 = persistent pipelined sweeps (default), 0 = one launch per 128-row block */
+/* triangular solves: 2 (default) = row-block streaming sweeps (one launch per direction, solved blocks published
+ * through the data), 1 = step-synchronous persistent sweeps, 0 = one launch per 128-row block */
 int updes_lu_set_solve_variant(UpdesLU *handle, int variant);
 /* test hook: rows the 32-wide register-resident panel holds (0 = default 148*640); smaller values
  * force the 16- / 8-wide base panels used for panels taller than 94 720 / 189 440 rows */
@@ -175,6 +195,9 @@ int64_t updes_launch_count(void);
  * 0 trailing-update GEMM, 1 panel, 2 row interchanges, 3 triangular base solve, 4 assembly, 5 solve. */
 int updes_profile_enable(int on);
 int updes_profile_read(int cat, double *ms, double *work, int64_t *count);
+/* tuning hook: columns per thread of the assembly kernel (bit 0: closed-form Laplacian rows 4 instead of 2;
+ * bit 1: general jets 2 instead of 4) */
+int updes_assemble_set_variant(int variant);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,9 @@ def cloud_arrays(c):
                 counts=np.array([c.N, c.Ni, c.Nd, c.Nn, c.Nr]), Np=np.array(c.Np, dtype=np.int64),
                 facet_names=np.array(names), facet_sizes=np.array([len(c.facet_nodes[k]) for k in names]),
                 facet_nodes=np.concatenate([np.asarray(c.facet_nodes[k], dtype=np.int64) for k in names]),
-                facet_types=np.array([c.facet_types[k] for k in names]))
+                facet_types=np.array([c.facet_types[k] for k in names]),
+                # original (grid / mesh) id of every sorted node: renumbering_map is old -> new (cloud.py:165)
+                old_of_new=np.array([o for o, _ in sorted(c.renumbering_map.items(), key=lambda kv: kv[1])], dtype=np.int64))
 
 
 c1 = O.RefSquareCloud(30, 20, {"South": "n", "West": "d", "North": "d", "East": "d"})

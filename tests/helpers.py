@@ -41,4 +41,5 @@ def cloud_from_golden(name):
     offs = np.concatenate([[0], np.cumsum(sizes)])
     facet_nodes = {nm: g["facet_nodes"][offs[k]:offs[k + 1]].tolist() for k, nm in enumerate(names)}
     facet_types = {nm: str(t) for nm, t in zip(names, g["facet_types"])}
-    return u.Cloud.from_arrays(g["sorted_nodes"], g["counts"], g["Np"], facet_types, facet_nodes, g["sorted_outward_normals"]), g
+    return u.Cloud.from_arrays(g["sorted_nodes"], g["counts"], g["Np"], facet_types, facet_nodes, g["sorted_outward_normals"],
+                               old_of_new=g["old_of_new"] if "old_of_new" in g else None), g

@@ -17,6 +17,7 @@ class NumpyBackend:
         self.ipiv = np.zeros(self.n, dtype=np.int32)
         self.info = 0
         self.calls = []
+        self.scale = None
 
     def fill_from_global(self, K):
         for j in self.layout.local_blocks(self.rank):
@@ -80,7 +81,27 @@ class NumpyBackend:
         return torch.from_numpy(np.array(host_array, dtype=np.float64))
 
     def permute_rhs(self, b):
-        return torch.from_numpy(b.numpy()[self.perm].copy())
+        v = b.numpy() if self.scale is None else b.numpy() * self.scale
+        return torch.from_numpy(v[self.perm].copy())
+
+    def row_absmax(self):
+        return torch.from_numpy(np.abs(self.local[:, :self.cols]).max(axis=1) if self.cols else np.zeros(self.n))
+
+    def apply_row_scale(self, absmax):
+        m = absmax.numpy()
+        sc = np.ones(self.n)
+        ok = (m > 0) & np.isfinite(m)
+        sc[ok] = np.ldexp(1.0, 1 - np.frexp(m[ok])[1])
+        self.scale = sc
+        self.local *= sc[:, None]
+
+    def event(self):
+        import time
+
+        class _E:
+            def __init__(self): self.t = time.perf_counter()
+            def elapsed_time(self, other): return (other.t - self.t) * 1e3
+        return _E()
 
     def block_sweep(self, upper, r0, lc, w, x):
         xv = x.numpy()

@@ -63,6 +63,49 @@ def test_block_cyclic_lu_matches_lapack(tmp_path, world, n, nb):
     assert [int(v) // nb for v in r["panels_r1"]] == list(range(1, (n + nb - 1) // nb, world))
 
 
+def _worker_equil(rank, world, port, n, nb, out):
+    """Row equilibration + timeline + a sub-group whose ranks differ from the global ranks."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from numpy_backend import NumpyBackend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        group = dist.new_group([1, 2])           # global ranks 1, 2 -> group ranks 0, 1; rank 0 sits out
+        if rank == 0:
+            return
+        grank = dist.get_rank(group)
+        rng = np.random.default_rng(3)
+        K = rng.normal(size=(n, n)) * (10.0 ** rng.integers(-6, 7, size=n))[:, None]     # rows of wildly different scale
+        b = rng.normal(size=n)
+        layout = ColumnBlockCyclic(n, nb, 2)
+        be = NumpyBackend(layout, grank)
+        be.fill_from_global(K)
+        lu = DistributedLU(layout, grank, be, group=group)
+        lu.timeline = []
+        lu.equilibrate().factor()
+        x = lu.solve(b).numpy().copy()
+        tl = lu.timeline_ms()
+        if grank == 0:
+            np.savez(out, x=x, K=K, b=b, scale=be.scale, nrec=len(tl), keys=sorted(set().union(*[set(r) for r in tl])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_equilibrated_lu_on_a_subgroup_with_timeline(tmp_path):
+    out = str(tmp_path / "res.npz")
+    n, nb = 150, 32
+    mp.spawn(_worker_equil, args=(3, _free_port(), n, nb, out), nprocs=3, join=True)
+    r = np.load(out)
+    K, b = r["K"], r["b"]
+    assert np.allclose(r["x"], np.linalg.solve(K, b), rtol=1e-9, atol=1e-12)
+    # exact powers of two that bring every row's largest magnitude into [1, 2)
+    m = np.abs(K).max(axis=1) * r["scale"]
+    assert np.all((m >= 1.0) & (m < 2.0)) and np.all(np.frexp(r["scale"])[0] == 0.5)
+    assert int(r["nrec"]) == (n + nb - 1) // nb
+    assert {"k", "wait", "update"} <= set(r["keys"].tolist()) and "panel" in r["keys"].tolist()
+
+
 def test_layout_maps():
     L = ColumnBlockCyclic(1000, 64, 4)
     assert L.nblocks == 16 and L.width(15) == 40

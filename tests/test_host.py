@@ -3,6 +3,7 @@ lowering, BC preparation, row descriptors, and that the C-ABI library loads and 
 symbol declared in include/updes_b200.h (no compute calls without a GPU)."""
 import os
 import re
+import sys
 from functools import partial
 
 import numpy as np
@@ -248,3 +249,125 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.updes_assemble_rows(0, 1.0, 10, 3, None, ctypes.byref(rows), 0, 1, 7, None, 16, None) == -5   # no centres
     assert lib.updes_eval_jets(0, 1.0, 0, 3, None, None, 0, 1, None, 1, None, None, None, None, None) == -3
     assert lib.updes_lu_set_gemm_variant(None, 0) == -1
+
+
+# ---- round 2: boundary semantics ------------------------------------------------------------------
+def test_steadysol_behaves_like_the_reference_namedtuple():
+    """utils.py:148: SteadySol = namedtuple('PDESolution', ['vals', 'coeffs', 'mat']); mat is lazy here."""
+    calls = []
+    sol = u.SteadySol(np.arange(3.0), np.arange(4.0), None, lambda: calls.append(1) or np.eye(2))
+    assert sol._fields == ("vals", "coeffs", "mat") and len(sol) == 3
+    assert np.array_equal(sol[0], np.arange(3.0)) and np.array_equal(sol[1], np.arange(4.0)) and np.array_equal(sol[-3], sol.vals)
+    assert calls == []                                   # nothing computed so far
+    v, c, m = sol                                         # unpacking reads mat
+    assert np.array_equal(m, np.eye(2)) and calls == [1]
+    assert np.array_equal(sol[2], np.eye(2)) and np.array_equal(sol.mat, np.eye(2)) and calls == [1]    # cached
+    sol2 = sol._replace(vals=np.zeros(3))
+    assert np.array_equal(sol2.vals, np.zeros(3)) and sol2.coeffs is sol.coeffs and np.array_equal(sol2.mat, np.eye(2))
+    assert set(sol._asdict()) == {"vals", "coeffs", "mat"}
+    with pytest.raises(IndexError):
+        sol[3]
+    with pytest.raises(ValueError):
+        sol._replace(values=1)
+    assert len(sol[0:2]) == 2
+    # a lazy mat stays lazy through _replace, and eager construction works as on the namedtuple
+    lazy = u.SteadySol(1, 2, None, lambda: calls.append(2) or 7)._replace(coeffs=3)
+    assert calls == [1] and lazy.mat == 7 and calls == [1, 2]
+    assert u.SteadySol(1, 2, 3).mat == 3
+
+
+def test_operator_with_per_node_python_control_flow_falls_back_to_row_evaluation():
+    """The reference vmaps operators over nodes (assembly.py:126-130): x is a (2,) point there.  A Python
+    `if` on a coordinate cannot run on the batched (2, Ni) coordinates; it is evaluated node by node."""
+    cloud = u.SquareCloud(Nx=9, Ny=7, facet_types=CONFIG1_FACETS)
+    seen_shapes = set()
+
+    def op(x, center, rbf, monomial, fields):
+        seen_shapes.add(np.shape(x))
+        k = 2.0 if x[0] > 0.5 else 1.0                      # ambiguous for an array -> ValueError in batch mode
+        return k * u.nodal_laplacian(x, center, rbf, monomial) + float(fields[0]) * u.nodal_value(x, center, rbf, monomial)
+
+    f = np.linspace(1, 2, cloud.N)
+    cphi, cpol = u.lower_diff_operator(op, cloud, u.polyharmonic, [f])
+    xs = cloud.sorted_nodes[:cloud.Ni, 0]
+    want = np.where(xs > 0.5, 2.0, 1.0)
+    assert np.array_equal(cphi[:, 3], want) and np.array_equal(cphi[:, 4], want) and np.allclose(cphi[:, 0], f[:cloud.Ni])
+    assert np.array_equal(cphi, cpol)
+    assert (2,) in seen_shapes and (2, cloud.Ni) in seen_shapes
+    # an operator that is wrong in BOTH modes still raises the explicit lowering error
+    with pytest.raises(u.OperatorLoweringError):
+        u.lower_diff_operator(lambda x, c, r, m, fl: (1.0 if float(x[0]) > 0 else 2.0) * u.nodal_value(x, c, r, m) ** 2,
+                              cloud, u.polyharmonic)
+
+
+def test_diff_args_of_coefficient_length_and_bad_lengths():
+    cloud = u.SquareCloud(Nx=8, Ny=6, facet_types=CONFIG1_FACETS)
+    op = lambda x, c, r, m, f: f[0] * u.nodal_value(x, c, r, m)
+    long_field = np.arange(cloud.N + 3, dtype=float)         # a coefficient vector (N+M): the reference indexes fields[i]
+    c, _ = u.lower_diff_operator(op, cloud, u.polyharmonic, [long_field])
+    assert np.array_equal(c[:, 0], long_field[:cloud.Ni])
+    with pytest.raises(ValueError):
+        u.lower_diff_operator(op, cloud, u.polyharmonic, [np.zeros(cloud.Ni - 1)])
+
+
+def test_points_layouts_inside_and_outside_operators():
+    from updes_b200 import operators as ops
+    pts, lay = ops._points(np.array([0.1, 0.2]))
+    assert lay == "single" and pts.shape == (1, 2)
+    pts, lay = ops._points(np.zeros((7, 2)))
+    assert lay == "rows" and pts.shape == (7, 2)
+    x = ops.BatchPoints(np.arange(10.0).reshape(2, 5))
+    pts, lay = ops._points(x)
+    assert lay == "batch" and pts.shape == (5, 2) and np.array_equal(pts[:, 0], np.arange(5.0))
+    rebuilt = np.stack([x[0], x[1]])                      # the usual port of jnp.array([x[0], x[1]]): loses the type
+    with pytest.raises(ValueError):
+        ops._points(rebuilt)                              # outside an operator call a (2, 5) array is ambiguous -> refuse
+    with ops._batch_rows(5):
+        pts, lay = ops._points(rebuilt)
+        assert lay == "batch" and np.array_equal(pts[:, 1], np.arange(5.0, 10.0))
+    with pytest.raises(ValueError):
+        ops._points(np.zeros(3))
+
+
+def test_interpolate_field_is_the_reference_permutation():
+    """updes/tests/test_interpolation.py:60-63 restated: two clouds on the same grid with swapped boundary types."""
+    f1 = {"South": "d", "West": "d", "North": "n", "East": "d"}
+    f2 = {"South": "n", "West": "n", "North": "d", "East": "n"}
+    c1 = u.SquareCloud(Nx=8, Ny=8, facet_types=f1)
+    c2 = u.SquareCloud(Nx=8, Ny=8, facet_types=f2)
+    field1 = np.sin(3 * c1.sorted_nodes[:, 0]) + c1.sorted_nodes[:, 1] ** 2
+    field2 = u.interpolate_field(field1, c1, c2)
+    assert np.allclose(field2, np.sin(3 * c2.sorted_nodes[:, 0]) + c2.sorted_nodes[:, 1] ** 2, atol=1e-12)
+    assert np.array_equal(u.interpolate_field(field2, c2, c1), field1)
+    vec = np.stack([field1, -field1], axis=-1)             # (N, 2) fields are carried row-wise (gradphi in the NS demo)
+    assert np.array_equal(u.interpolate_field(vec, c1, c2)[:, 1], -field2)
+    # the committed parse of the reference's mesh fixture keeps its original numbering too
+    from helpers import cloud_from_golden
+    cv, _ = cloud_from_golden("mesh_msh_cloud_vel.npz")
+    cp, _ = cloud_from_golden("mesh_msh_cloud_phi.npz")
+    xv = u.interpolate_field(cp.sorted_nodes, cp, cv)
+    assert np.array_equal(xv, cv.sorted_nodes)
+
+
+def test_config3_operators_lower_to_the_reference_rows():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import configs
+    from helpers import cloud_from_golden
+    cv, _ = cloud_from_golden("mesh_msh_cloud_vel.npz")
+    du, ru, dv, rv, dphi, rphi = configs.config3_operators(u, Re=100.0)
+    uu, vv = np.cos(cv.sorted_nodes[:, 0]), np.sin(cv.sorted_nodes[:, 1])
+    c, cp = u.lower_diff_operator(du, cv, u.polyharmonic, [uu, vv])
+    assert np.array_equal(c[:, 1], uu[:cv.Ni]) and np.array_equal(c[:, 2], vv[:cv.Ni]) and np.all(c[:, 3:] == -0.01) and np.all(c[:, 0] == 0)
+    assert np.array_equal(c, cp)
+    c, _ = u.lower_diff_operator(dphi, cv, u.polyharmonic, None)
+    assert np.array_equal(c, np.tile([0, 0, 0, 1.0, 1.0], (cv.Ni, 1)))
+
+
+def test_distributed_path_is_opt_in():
+    """An initialised process group alone must not switch pde_solver to the sharded path."""
+    from updes_b200 import operators as ops
+    assert ops._dist_world() == (1, 0, None)
+    with pytest.raises(RuntimeError):
+        u.enable_distributed()                           # no process group
+    with pytest.raises(RuntimeError):
+        ops._dist_world(distributed=True)

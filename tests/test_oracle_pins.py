@@ -170,3 +170,57 @@ def test_golden_solution_vectors_match_reference_formulation(oracle):
     c = np.linalg.solve(K, np.concatenate([g["q"], np.zeros(3)]))
     A = oracle.assemble_A(cloud, "polyharmonic", 1, 3)
     assert np.max(np.abs(A[:cloud.N] @ c - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))
+
+
+# ---- second, independent pin: 50-digit numerical differentiation of the kernels' DEFINITIONS -----
+def _mp_kernel(kind, param):
+    """The reference's kernel definitions (updes/utils.py:19-69) transcribed for mpmath: functions of (x, y; cx, cy)."""
+    import mpmath as mp
+    r = lambda x, y, cx, cy: mp.sqrt((x - cx) ** 2 + (y - cy) ** 2)            # utils.py:19-22
+    if kind == "polyharmonic":
+        return lambda x, y, cx, cy: r(x, y, cx, cy) ** (2 * int(param) + 1)     # utils.py:50-55
+    if kind == "thin_plate":
+        return lambda x, y, cx, cy: mp.log(r(x, y, cx, cy)) * r(x, y, cx, cy) ** (2 * int(param))   # utils.py:63-69
+    if kind == "gaussian":
+        return lambda x, y, cx, cy: mp.exp(-(mp.mpf(param) * r(x, y, cx, cy)) ** 2)     # utils.py:44-48
+    if kind == "multiquadric":
+        return lambda x, y, cx, cy: mp.sqrt(1 + (mp.mpf(param) * r(x, y, cx, cy)) ** 2)   # utils.py:30-35
+    return lambda x, y, cx, cy: 1 / mp.sqrt(1 + (mp.mpf(param) * r(x, y, cx, cy)) ** 2)   # utils.py:37-42
+
+
+def _mp_jet(kind, param, x, c):
+    """(phi, phi_x, phi_y, phi_xx, phi_yy) w.r.t. the evaluation point by 50-digit numerical differentiation."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    f = _mp_kernel(kind, param)
+    X, Y, CX, CY = (mp.mpf(float(v)) for v in (x[0], x[1], c[0], c[1]))
+    fx = lambda a: f(a, Y, CX, CY)
+    fy = lambda b: f(X, b, CX, CY)
+    return [f(X, Y, CX, CY), mp.diff(fx, X, 1), mp.diff(fy, Y, 1), mp.diff(fx, X, 2), mp.diff(fy, Y, 2)]
+
+
+@pytest.mark.parametrize("kind,param", KERNELS)
+def test_closed_form_jets_match_50_digit_differentiation(oracle, kind, param):
+    """The C closed forms against an arithmetic path that shares nothing with them: mpmath (50 digits) numerical
+    differentiation of the kernel definition.  TRUE per-entry relative error <= 1e-12 wherever the entry is
+    not a near-cancellation; points close to the sign change of the gaussian Laplacian terms (r ~ 1/eps) and very
+    small / large r are included on purpose, there the error is measured against the jet's largest component."""
+    rng = np.random.default_rng(11)
+    pts = [(rng.uniform(0, 1, 2), rng.uniform(0, 1, 2)) for _ in range(12)]
+    pts.append((np.array([0.3, 0.4]), np.array([0.3 + 1e-7, 0.4 - 2e-7])))              # tiny r
+    pts.append((np.array([0.0, 0.0]), np.array([1.0, 1.0])))                            # largest r on the unit square
+    if kind in ("gaussian", "multiquadric", "inverse_multiquadric"):
+        rr = 1.0 / float(param)                                                           # phi_xx of the gaussian changes sign near dx = 1/(sqrt(2) eps)
+        pts.append((np.array([0.2, 0.2]), np.array([0.2 + rr / np.sqrt(2.0), 0.2])))
+        pts.append((np.array([0.2, 0.2]), np.array([0.2 + rr / np.sqrt(2.0) * (1 + 1e-6), 0.2 + 1e-9])))
+    worst_true, worst_scaled = 0.0, 0.0
+    for x, c in pts:
+        got = oracle.rbf_jet(kind, param, x, c)
+        want = [float(v) for v in _mp_jet(kind, param, x, c)]
+        scale = max(abs(v) for v in want)
+        for g, w in zip(got, want):
+            worst_scaled = max(worst_scaled, abs(g - w) / scale)
+            if abs(w) > 1e-6 * scale:
+                worst_true = max(worst_true, abs(g - w) / abs(w))
+    assert worst_scaled <= 1e-13, (kind, param, worst_scaled)
+    assert worst_true <= 2e-10, (kind, param, worst_true)      # entries down to 1e-6 of the jet scale keep >= 4 extra digits

@@ -9,6 +9,7 @@ from .cloud import Cloud, GmshCloud, SquareCloud
 from .rbf import (compute_nb_monomials, distance, gaussian, identify_rbf, inverse_multiquadric, make_all_monomials,
                   make_monomial, multiquadric, polyharmonic, thin_plate)
 from .operators import (BatchPoints, OperatorLoweringError, SteadySol, boundary_conditions_func_to_arr, clear_cache,
+                        disable_distributed, enable_distributed, interpolate_field,
                         compute_coefficients, core_compute_coefficients, divergence, divergence_vec, dot,
                         duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vec, laplacian,
                         laplacian_vec, lower_diff_operator, nodal_div_grad, nodal_gradient, nodal_laplacian,

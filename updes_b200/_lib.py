@@ -32,6 +32,12 @@ SIGNATURES = {
     "updes_lu_create": (_I32, [ctypes.POINTER(_VP), _I64, _I64]),
     "updes_lu_destroy": (_I32, [_VP]),
     "updes_lu_factor": (_I32, [_VP, _VP, _VP, _VP, _VP]),
+    "updes_lu_factor_scaled": (_I32, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "updes_row_absmax": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP]),
+    "updes_scale_from_absmax": (_I32, [_VP, _I64, _VP, _VP]),
+    "updes_row_scale": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP]),
+    "updes_lu_set_row_scale": (_I32, [_VP, _VP]),
+    "updes_lu_status": (_I32, [_VP, ctypes.POINTER(ctypes.c_int32), _VP]),
     "updes_lu_solve": (_I32, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
     "updes_dgemm_sub": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "updes_lu_panel": (_I32, [_VP, _VP, _I64, _I64, _VP, _VP, _VP]),
@@ -51,6 +57,7 @@ SIGNATURES = {
     "updes_b200_version": (ctypes.c_char_p, []),
     "updes_launch_count": (_I64, []),
     "updes_profile_enable": (_I32, [_I32]),
+    "updes_assemble_set_variant": (_I32, [_I32]),
     "updes_profile_read": (_I32, [_I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 }
 

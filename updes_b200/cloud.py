@@ -75,7 +75,7 @@ class Cloud:
             self.outward_normals = {}
 
     @classmethod
-    def from_arrays(cls, sorted_nodes, counts, Np, facet_types, facet_nodes, sorted_outward_normals):
+    def from_arrays(cls, sorted_nodes, counts, Np, facet_types, facet_nodes, sorted_outward_normals, old_of_new=None):
         """Cloud from already-renumbered arrays (user-supplied point sets, or clouds built elsewhere).
 
         ``counts`` = (N, Ni, Nd, Nn, Nr); ``facet_types`` must already carry the reference's suffix on
@@ -98,7 +98,13 @@ class Cloud:
             for i in ids:
                 types[i] = self.facet_types[f]
         self.node_types = dict(enumerate(types))
-        self.renumbering_map = {i: i for i in range(self.N)}
+        # old_of_new[i] = original (mesh / grid) id of sorted node i; lets interpolate_field relate two clouds
+        # built on the same nodes with different boundary types
+        oon = np.arange(self.N) if old_of_new is None else np.asarray(old_of_new, dtype=np.int64)
+        self._old_of_new = oon
+        self._new_of_old = np.empty(self.N, dtype=np.int64)
+        self._new_of_old[oon] = np.arange(self.N)
+        self.renumbering_map = {int(o): int(k) for k, o in enumerate(oon)}     # old -> new, in new-id order (cloud.py:165)
         return self
 
     @property

@@ -20,10 +20,11 @@ constexpr int ASM_THREADS = 256;
 // n = 90 003), 4 for general jets (FP64/LSU-bound: fewer row-descriptor loads per entry, 18.3 ms vs 20.5 ms)
 constexpr int ASM_TR = 32;               // rows per tile
 
-struct RowStage {
+struct alignas(16) RowStage {
   RowPoint a, b;
   int has_b;
   int skip;
+  int pad[2];
 };
 
 struct AsmParams {
@@ -37,26 +38,38 @@ struct AsmParams {
   double e2;
 };
 
-__device__ __forceinline__ void load_point(RowPoint &rp, const double *pts, int p, const double *c) {
+// stage one evaluation point of a row: coordinates + coefficients with the kernel's constants folded in
+template <int MASK>
+__device__ __forceinline__ void load_point(RowPoint &rp, const double *pts, int p, const double *c, double gamma,
+                                           double eta, double lapfac) {
   rp.x = pts[2 * (size_t)p];
   rp.y = pts[2 * (size_t)p + 1];
-  rp.c0 = c[0]; rp.c1 = c[1]; rp.c2 = c[2]; rp.c3 = c[3]; rp.c4 = c[4];
-  rp.c34 = c[3] + c[4];
+  rp.c0 = c[0];
+  if (MASK & JET_ISO) {
+    rp.cg1 = 0.0; rp.cg2 = 0.0; rp.cg34 = 0.0; rp.ch4 = 0.0;
+    rp.ch3 = lapfac * c[3];
+  } else {
+    rp.cg1 = gamma * c[1]; rp.cg2 = gamma * c[2]; rp.cg34 = gamma * (c[3] + c[4]);
+    rp.ch3 = eta * c[3]; rp.ch4 = eta * c[4];
+  }
 }
 
-template <int KIND, int MASK, int ASM_CPT>
+template <int KIND, int MASK, int ASM_CPT, int PFIX>
 __global__ void __launch_bounds__(ASM_THREADS) assemble_phi_kernel(AsmParams P) {
   constexpr int ASM_TC = ASM_THREADS * ASM_CPT;   // columns per tile
   __shared__ RowStage stage[ASM_TR];
   const long long r_tile = P.row0 + (long long)blockIdx.y * ASM_TR;
   const int nr = (int)min((long long)ASM_TR, P.row0 + P.nrows - r_tile);
+  double gamma, eta, lapfac;
+  hat_constants<KIND>(P.ip, P.e2, gamma, eta, lapfac);
+  const double gamma2 = 2.0 * gamma;
   if (threadIdx.x < nr) {
     const long long r = r_tile + threadIdx.x;
     RowStage st;
-    load_point(st.a, P.rows.pts, P.rows.p1[r], P.rows.cphi1 + 5 * r);
+    load_point<MASK>(st.a, P.rows.pts, P.rows.p1[r], P.rows.cphi1 + 5 * r, gamma, eta, lapfac);
     const int p2 = P.rows.p2 ? P.rows.p2[r] : -1;
     st.has_b = p2 >= 0;
-    if (st.has_b) load_point(st.b, P.rows.pts, p2, P.rows.cphi2 + 5 * r);
+    if (st.has_b) load_point<MASK>(st.b, P.rows.pts, p2, P.rows.cphi2 + 5 * r, gamma, eta, lapfac);
     else st.b = st.a;
     st.skip = P.rows.skip ? P.rows.skip[r] : -1;
     stage[threadIdx.x] = st;
@@ -78,20 +91,17 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_phi_kernel(AsmParams P) 
   if (j >= jend) return;
   double *o = P.out + (r_tile - P.row0) * P.ld + (j - P.col0);
   const int ncol = (int)min((long long)ASM_CPT, jend - j);
+  const int j32 = (int)j;
 #pragma unroll 2
   for (int t = 0; t < nr; t++) {
     const RowStage &st = stage[t];
     double v[ASM_CPT];
 #pragma unroll
-    for (int u = 0; u < ASM_CPT; u++) v[u] = entry_one_point<KIND, MASK>(st.a, cx[u], cy[u], P.ip, P.e2);
+    for (int u = 0; u < ASM_CPT; u++) v[u] = entry_one_point<KIND, MASK, PFIX>(st.a, cx[u], cy[u], P.ip, P.e2, gamma2, eta);
     if (st.has_b) {
 #pragma unroll
-      for (int u = 0; u < ASM_CPT; u++) v[u] += entry_one_point<KIND, MASK>(st.b, cx[u], cy[u], P.ip, P.e2);
+      for (int u = 0; u < ASM_CPT; u++) v[u] += entry_one_point<KIND, MASK, PFIX>(st.b, cx[u], cy[u], P.ip, P.e2, gamma2, eta);
     }
-    const int sk = st.skip - (int)j;                 // skipped column relative to this thread's first column
-#pragma unroll
-    for (int u = 0; u < ASM_CPT; u++)
-      if (sk == u) v[u] = 0.0;
     if (ncol == ASM_CPT) {
 #pragma unroll
       for (int u = 0; u < ASM_CPT; u += 2) __stcs(reinterpret_cast<double2 *>(o + u), make_double2(v[u], v[u + 1]));
@@ -100,6 +110,11 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_phi_kernel(AsmParams P) 
       for (int u = 0; u < ASM_CPT; u++)
         if (u < ncol) __stcs(o + u, v[u]);
     }
+    // skipped column (the row's own node, cloud.py:110-112): the one thread that holds it overwrites the
+    // entry with 0 after its vector store (same thread, same address: program order) -- one predicated
+    // store instead of a select per entry
+    const unsigned int sk = (unsigned int)(st.skip - j32);
+    if (sk < (unsigned int)ncol) __stcs(o + sk, 0.0);
     o += P.ld;
   }
 }
@@ -161,24 +176,45 @@ __global__ void assemble_pt_rows_kernel(PtParams P) {
   }
 }
 
+// columns per thread: g_asm_variant bit 0 -> closed-form Laplacian rows use 4 (default 2);
+//                     bit 1 -> general jets use 2 (default 4)
+static int g_asm_variant = 0;
+
+template <int KIND, int MASK, int CPT>
+static void launch_phi_one(const AsmParams &P, cudaStream_t st) {
+  dim3 grid((unsigned)((P.ncols + ASM_THREADS * CPT - 1) / (ASM_THREADS * CPT)), (unsigned)((P.nrows + ASM_TR - 1) / ASM_TR));
+  // the default kernel r^3 (polyharmonic a = 1) gets its exponent at compile time: no per-entry branches on `a`
+  if (KIND == UPDES_RBF_POLYHARMONIC && P.ip == 1) assemble_phi_kernel<KIND, MASK, CPT, 3><<<grid, ASM_THREADS, 0, st>>>(P);
+  else assemble_phi_kernel<KIND, MASK, CPT, 0><<<grid, ASM_THREADS, 0, st>>>(P);
+}
+
 template <int KIND>
 static int launch_phi(int mask, const AsmParams &P, cudaStream_t st) {
-  const unsigned gy = (unsigned)((P.nrows + ASM_TR - 1) / ASM_TR);
   if (mask & JET_ISO) {
-    dim3 grid((unsigned)((P.ncols + ASM_THREADS * 2 - 1) / (ASM_THREADS * 2)), gy);
-    if (mask & JET_VAL) assemble_phi_kernel<KIND, JET_ISO | JET_VAL, 2><<<grid, ASM_THREADS, 0, st>>>(P);
-    else assemble_phi_kernel<KIND, JET_ISO, 2><<<grid, ASM_THREADS, 0, st>>>(P);
+    const bool wide = g_asm_variant & 1;
+    if (mask & JET_VAL) {
+      if (wide) launch_phi_one<KIND, JET_ISO | JET_VAL, 4>(P, st); else launch_phi_one<KIND, JET_ISO | JET_VAL, 2>(P, st);
+    } else {
+      if (wide) launch_phi_one<KIND, JET_ISO, 4>(P, st); else launch_phi_one<KIND, JET_ISO, 2>(P, st);
+    }
     UPDES_LAUNCH_CHECK();
     return 0;
   }
-  dim3 grid((unsigned)((P.ncols + ASM_THREADS * 4 - 1) / (ASM_THREADS * 4)), gy);
+  const bool narrow = g_asm_variant & 2;
+#define UPDES_PHI_CASE(M)                                                          \
+  case M:                                                                          \
+    if (narrow) launch_phi_one<KIND, M, 2>(P, st); else launch_phi_one<KIND, M, 4>(P, st); \
+    break;
   switch (mask & 7) {
-    case 1: assemble_phi_kernel<KIND, 1, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 2: assemble_phi_kernel<KIND, 2, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 3: assemble_phi_kernel<KIND, 3, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    case 6: assemble_phi_kernel<KIND, 6, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
-    default: assemble_phi_kernel<KIND, 7, 4><<<grid, ASM_THREADS, 0, st>>>(P); break;
+    UPDES_PHI_CASE(1)
+    UPDES_PHI_CASE(2)
+    UPDES_PHI_CASE(3)
+    UPDES_PHI_CASE(6)
+    default:
+      if (narrow) launch_phi_one<KIND, 7, 2>(P, st); else launch_phi_one<KIND, 7, 4>(P, st);
+      break;
   }
+#undef UPDES_PHI_CASE
   UPDES_LAUNCH_CHECK();
   return 0;
 }
@@ -247,4 +283,11 @@ extern "C" int updes_assemble_block(int rbf_kind, double rbf_param, int N, int M
                                     int64_t ncols, int jet_mask, double *out, int64_t ld, void *stream) {
   return updes::assemble_block_impl(rbf_kind, rbf_param, N, M, centres, rows, row0, nrows, col0, ncols, jet_mask, out,
                                     ld, (cudaStream_t)stream);
+}
+
+/* tuning hook (tools/, bench experiments): columns per thread of the assembly kernel, see g_asm_variant */
+extern "C" int updes_assemble_set_variant(int variant) {
+  if (variant < 0 || variant > 3) return -1;
+  updes::g_asm_variant = variant;
+  return 0;
 }

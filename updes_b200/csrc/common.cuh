@@ -48,20 +48,33 @@ __device__ __forceinline__ double ipow_u(double x, int e) {
   return v;
 }
 
-// 1/sqrt(s) in FP64 from the FP32 SFU estimate plus one third-order (Halley) correction:
-// 23 bits -> ~69 bits before rounding, about 1 ulp, in 5 FP64 operations instead of the ~12 of
-// rsqrt().  Falls back to rsqrt() outside the float range.
-__device__ __forceinline__ double fast_rsqrt(double s) {
-  // range test on the exponent bits (integer pipe, keeps the FP64 pipe for arithmetic):
-  // 2^-100 <= s < 2^100, which also excludes 0, negatives, inf and NaN
-  const unsigned int hi = (unsigned int)__double2hiint(s);
-  if (hi - 0x39B00000u >= 0x0C800000u) return rsqrt(s);
-  const double y = (double)rsqrtf((float)s);
+// 1/sqrt(s) in FP64 from the SFU's FP64 estimate (MUFU.RSQ64H: works on the high word of the double, so
+// no FP64<->FP32 conversions; ~2^-20 relative after the truncation) plus one third-order (Halley)
+// correction: (5/16) e^3 ~ 2^-63 before rounding, i.e. about 1 ulp, in 5 FP64 operations instead of the
+// ~12 of rsqrt().  `s` must be a positive normal double.
+__device__ __forceinline__ double fast_rsqrt_pos(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
   const double t = s * y;
   const double e = fma(-t, y, 1.0);
   const double q = e * fma(0.375, e, 0.5);
   return fma(y, q, y);
 }
+// Same for s >= 0 with the seed's input clamped to >= 2^-1021 on the integer pipe: the result stays finite at
+// s == 0 (~2^511), so expressions of the form s * rsqrt(s) evaluate to exactly 0 there without a select.
+__device__ __forceinline__ double fast_rsqrt_clamped(double s) {
+  const int hi = max(__double2hiint(s), 0x00200000);
+  const double sc = __hiloint2double(hi, 0);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sc));
+  const double t = s * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(y, q, y);
+}
+// s >= 0 that is zero or below 2^-1021 (integer pipe test on the exponent bits)
+__device__ __forceinline__ bool tiny_or_zero(double s) { return (unsigned int)__double2hiint(s) < 0x00200000u; }
+__device__ __forceinline__ double fast_rsqrt(double s) { return tiny_or_zero(s) ? rsqrt(s) : fast_rsqrt_pos(s); }
 
 // Radial triple of a kernel as a function of s = r^2 > 0:
 //   phi(r),  g = phi'(r)/r,  h = (phi''(r) - g)/r^2
@@ -101,13 +114,13 @@ __device__ __forceinline__ void radial(double s, int ip, double e2, double &phi,
     h = 4.0 * e2 * e2 * E;
   } else if (KIND == UPDES_RBF_MULTIQUADRIC) {
     const double w = fma(e2, s, 1.0);
-    const double rw = rsqrt(w);
+    const double rw = fast_rsqrt_pos(w);
     phi = w * rw;
     g = e2 * rw;
     h = -(e2 * e2) * (rw * rw * rw);
   } else {  // inverse multiquadric
     const double w = fma(e2, s, 1.0);
-    const double rw = rsqrt(w);
+    const double rw = fast_rsqrt_pos(w);
     const double rw3 = rw * rw * rw;
     phi = rw;
     g = -e2 * rw3;
@@ -140,33 +153,102 @@ __device__ __forceinline__ double phi_at_zero() {
   return (KIND == UPDES_RBF_POLYHARMONIC || KIND == UPDES_RBF_THIN_PLATE) ? 0.0 : 1.0;
 }
 
-// Pre-combined coefficients of one evaluation point of one row:
-//   entry = c0 phi + g (c1 dx + c2 dy + c34) + h (c3 dx^2 + c4 dy^2),  c34 = c3 + c4
-struct RowPoint {
+// ---- assembly entry with constants folded into the row coefficients ---------------------------------
+// For every kernel the radial triple factors as  g = gamma * ghat,  h = eta * hhat  with constants
+// gamma, eta (polyharmonic p = 2a+1: gamma = p, eta = p(p-2), ghat = r^(p-2), hhat = r^(p-4); gaussian:
+// ghat = hhat = phi; ...).  The assembly kernel folds gamma / eta into the staged row coefficients once
+// per tile, so the per-entry work is only the "hat" triple and three fused dot products:
+//   entry = c0 phi + ghat (cg1 dx + cg2 dy + cg34) + hhat (ch3 dx^2 + ch4 dy^2)
+// Rows of the form c0 phi + c3 (phi_xx + phi_yy) (JET_ISO) use the radial Laplacian
+//   lap = 2 g + h s;   polyharmonic: lap = p^2 r^(p-2), p^2 folded into the coefficient.
+template <int KIND>
+__device__ __forceinline__ void hat_constants(int ip, double e2, double &gamma, double &eta, double &lapfac) {
+  if (KIND == UPDES_RBF_POLYHARMONIC) {
+    const int p = 2 * ip + 1;
+    gamma = (double)p; eta = (double)(p * (p - 2)); lapfac = (double)(p * p);
+  } else if (KIND == UPDES_RBF_GAUSSIAN) {
+    gamma = -2.0 * e2; eta = 4.0 * e2 * e2; lapfac = 1.0;
+  } else if (KIND == UPDES_RBF_MULTIQUADRIC) {
+    gamma = e2; eta = -(e2 * e2); lapfac = 1.0;
+  } else if (KIND == UPDES_RBF_INVERSE_MULTIQUADRIC) {
+    gamma = -e2; eta = 3.0 * (e2 * e2); lapfac = 1.0;
+  } else {
+    gamma = 1.0; eta = 1.0; lapfac = 1.0;
+  }
+}
+
+// (phi, ghat, hhat) for s > 0 (s not tiny)
+// PFIX: compile-time polyharmonic exponent (3 = the default r^3 kernel), 0 = runtime `ip`
+template <int KIND, int PFIX>
+__device__ __forceinline__ void radial_hat(double s, int ip, double e2, double &phi, double &gh, double &hh) {
+  if (KIND == UPDES_RBF_POLYHARMONIC) {
+    const int p = PFIX ? PFIX : 2 * ip + 1;
+    const double rs = PFIX == 3 ? fast_rsqrt_clamped(s) : fast_rsqrt_pos(s);
+    if (p == 3) hh = rs;
+    else if (p == 1) hh = rs * rs * rs;
+    else hh = ipow_u(s, (p - 5) >> 1) * (s * rs);
+    gh = hh * s;
+    phi = gh * s;
+  } else if (KIND == UPDES_RBF_GAUSSIAN) {
+    phi = exp(-e2 * s); gh = phi; hh = phi;
+  } else if (KIND == UPDES_RBF_MULTIQUADRIC) {
+    const double w = fma(e2, s, 1.0);
+    const double rw = fast_rsqrt_pos(w);
+    phi = w * rw; gh = rw; hh = rw * rw * rw;
+  } else if (KIND == UPDES_RBF_INVERSE_MULTIQUADRIC) {
+    const double w = fma(e2, s, 1.0);
+    const double rw = fast_rsqrt_pos(w);
+    const double rw2 = rw * rw;
+    phi = rw; gh = rw2 * rw; hh = gh * rw2;
+  } else {
+    radial<KIND>(s, ip, e2, phi, gh, hh);      // thin plate: no constant to fold
+  }
+}
+
+// One evaluation point of one row, coefficients already scaled by gamma / eta / lapfac.
+struct alignas(16) RowPoint {
   double x, y;
-  double c0, c1, c2, c3, c4, c34;
+  double ch3, c0;                           // JET_ISO rows: ch3 holds lapfac * c3 (one 16-byte load with c0)
+  double cg1, cg2, cg34, ch4;
 };
 
-template <int KIND, int MASK>
-__device__ __forceinline__ double entry_one_point(const RowPoint &rp, double cx, double cy, int ip, double e2) {
+template <int KIND, int MASK, int PFIX>
+__device__ __forceinline__ double entry_one_point(const RowPoint &rp, double cx, double cy, int ip, double e2,
+                                                  double gamma2, double eta) {
   const double dx = rp.x - cx, dy = rp.y - cy;
-  const double dx2 = dx * dx, dy2 = dy * dy;
-  const double s = dx2 + dy2;
+  const double dy2 = dy * dy;
   if (MASK & JET_ISO) {
-    double phi, lap;
-    radial_lap<KIND>(s, ip, e2, phi, lap);
-    double v = rp.c3 * lap;
-    if (MASK & JET_VAL) v = fma(rp.c0, phi, v);
-    return is_zero_bits(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
+    const double s = fma(dx, dx, dy2);
+    double v;
+    if (KIND == UPDES_RBF_POLYHARMONIC) {
+      const int p = PFIX ? PFIX : 2 * ip + 1;
+      const double rs = PFIX == 3 ? fast_rsqrt_clamped(s) : fast_rsqrt_pos(s);
+      double l;                                 // r^(p-2)
+      if (p == 3) l = s * rs;
+      else if (p == 1) l = rs;
+      else l = ipow_u(s, (p - 3) >> 1) * (s * rs);
+      v = rp.ch3 * l;
+      if (MASK & JET_VAL) v = fma(rp.c0 * s, l, v);
+    } else {
+      double phi, gh, hh;
+      radial_hat<KIND, PFIX>(s, ip, e2, phi, gh, hh);
+      v = rp.ch3 * fma(eta * hh, s, gamma2 * gh);   // lap = 2 g + h s
+      if (MASK & JET_VAL) v = fma(rp.c0, phi, v);
+    }
+    // r == 0: derivatives -> 0 (nan_to_num), value -> phi(0).  r^3: already exactly 0 (clamped seed).
+    if (KIND == UPDES_RBF_POLYHARMONIC && PFIX == 3) return v;
+    return tiny_or_zero(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
   }
-  double phi, g, h;
-  radial<KIND>(s, ip, e2, phi, g, h);
+  const double dx2 = dx * dx;
+  const double s = dx2 + dy2;
+  double phi, gh, hh;
+  radial_hat<KIND, PFIX>(s, ip, e2, phi, gh, hh);
   double v = 0.0;
-  if (MASK & JET_H) v = h * fma(rp.c3, dx2, rp.c4 * dy2);
-  if (MASK & JET_G) v = fma(g, fma(rp.c1, dx, fma(rp.c2, dy, rp.c34)), v);
+  if (MASK & JET_H) v = hh * fma(rp.ch3, dx2, rp.ch4 * dy2);
+  if (MASK & JET_G) v = fma(gh, fma(rp.cg1, dx, fma(rp.cg2, dy, rp.cg34)), v);
   if (MASK & JET_VAL) v = fma(rp.c0, phi, v);
-  // r == 0: derivatives -> 0 (nan_to_num), value -> phi(0)
-  return is_zero_bits(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
+  if (KIND == UPDES_RBF_POLYHARMONIC && PFIX == 3) return v;    // every term is exactly 0 at s == 0
+  return tiny_or_zero(s) ? ((MASK & JET_VAL) ? rp.c0 * phi_at_zero<KIND>() : 0.0) : v;
 }
 
 // jet of monomial id (utils.py:92-134) at (x, y): value, d/dx, d/dy, d2/dx2, d2/dy2

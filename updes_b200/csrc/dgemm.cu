@@ -425,7 +425,7 @@ extern "C" int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows) {
 
 extern "C" int updes_lu_set_panel_variant(UpdesLU *handle, int variant) {
   if (!handle) return -1;
-  if (variant < 0 || variant > 1) return -2;
+  if (variant < 0 || variant > 2) return -2;
   handle->panel_variant = variant;
   return 0;
 }

@@ -22,7 +22,8 @@ struct UpdesLU {
   int num_sms = 148;
   int gemm_ctas = 0;       // 0 = one CTA per SM; smaller leaves SMs free for concurrent NCCL kernels
   int64_t panel_cap = 0;   // rows a 32-wide register-resident panel can hold (0 = num_sms * 640); test hook
-  int panel_variant = 1;   // 1: short panels (<= 10 240 rows) use the thread-block-cluster kernel; 0: always the grid kernel
+  int panel_variant = 2;   // 2 (default): implicit-pivoting kernels (cluster push exchange for <= 8 192 rows, grid kernel above);
+                           // 1: first-generation cluster + grid kernels; 0: first-generation grid kernel only
   int gemm_kdeep = 1;      // 1 (default): 32-deep pipeline stages (two 16-k sub-tiles per barrier round) when k % 32 == 0
   int gemm_variant = 1;    // 1 (default): ping-pong, two 128x64 CTAs per SM; 0: one 128x128 CTA per SM
   MatView view[UPDES_MAX_VIEWS];
@@ -35,11 +36,14 @@ struct UpdesLU {
   unsigned int barrier_count = 0;  // host mirror of the counter after all enqueued panels
   unsigned int *gemm_counters = nullptr;   // ring of per-launch tile counters (dynamic scheduler)
   unsigned long long gemm_launch_id = 0;
-  int solve_variant = 1;           // 1: persistent pipelined sweeps (default); 0: one launch per 128-row block
+  int solve_variant = 2;           // 2: row-block streaming sweeps (default); 1: step-synchronous persistent sweeps; 0: one launch per 128-row block
+  unsigned int *sweep_ticket = nullptr;  // dynamic row-block counter of the streaming sweep (monotonic)
+  unsigned int sweep_ticket_count = 0;   // host mirror
   unsigned int *sweep_flags = nullptr;   // [ceil(n/128)] publication flags of the persistent sweep
   unsigned int sweep_epoch = 0;
   int *sweep_err = nullptr;
   int32_t *perm = nullptr;         // [n] row permutation of the last factorisation (for solves)
+  const double *row_scale = nullptr;   // [n] caller-owned row equilibration factors applied to right-hand sides, or null
   double *xbuf = nullptr;          // solve scratch
 };
 
@@ -64,6 +68,9 @@ int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int 
 int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t swap_lo, int64_t swap_hi,
                  int32_t *ipiv, int32_t *info, cudaStream_t st);
 int build_permutation(UpdesLU *h, const int32_t *ipiv, cudaStream_t st);
+int row_absmax(const double *A, int64_t rows, int64_t cols, int64_t ld, double *out, cudaStream_t st);
+int scale_from_absmax(const double *absmax, int64_t n, double *scale, cudaStream_t st);
+int row_scale(double *A, int64_t rows, int64_t cols, int64_t ld, const double *scale, cudaStream_t st);
 int rank8_update(UpdesLU *h, int v, int64_t ra, int64_t ca, int64_t rb, int64_t cb, int64_t rc, int64_t cc, int64_t m,
                  int nc, cudaStream_t st);
 

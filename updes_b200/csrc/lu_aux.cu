@@ -153,6 +153,85 @@ int rank8_update(UpdesLU *h, int v, int64_t ra, int64_t ca, int64_t rb, int64_t 
   return 0;
 }
 
+// ---- row equilibration ------------------------------------------------------------------------------
+// The collocation matrix mixes rows of very different scales (operator rows ~ 9 r or 1/DT, boundary rows
+// ~ r^3, polynomial rows ~ 1; SURVEY.md section 7, hard part 3).  Partial pivoting compares entries across rows, so
+// the rows are first brought to max |entry| in [1, 2) by an exact power-of-two factor (no rounding: the
+// scaled matrix is exactly diag(s) K); the solve scales the right-hand side by the same factors.
+// One warp per row, 16-byte accesses; HBM-bound (the matrix is read once and read + written once).
+__global__ void __launch_bounds__(256) row_absmax_kernel(const double *A, long long rows, long long cols, long long ld,
+                                                         double *out) {
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const double *row = A + r * ld;
+  double m = 0.0;
+  const long long c2 = cols & ~1LL;
+  for (long long c = 2LL * lane; c < c2; c += 64) {
+    const double2 v = *reinterpret_cast<const double2 *>(row + c);
+    const double a0 = fabs(v.x), a1 = fabs(v.y);
+    m = a0 > m ? a0 : m;                // NaN never raises the maximum
+    m = a1 > m ? a1 : m;
+  }
+  if (lane == 0 && c2 < cols) { const double a0 = fabs(row[c2]); m = a0 > m ? a0 : m; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, m, off);
+    m = o > m ? o : m;
+  }
+  if (lane == 0) out[r] = m;
+}
+
+// scale[r] = 2^-floor(log2(absmax[r])) (1 for zero / non-finite rows): exponent arithmetic only
+__global__ void scale_from_absmax_kernel(const double *absmax, long long n, double *scale) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = absmax[i];
+  double sc = 1.0;
+  if (m > 0.0 && m < 1.7976931348623157e308) {
+    int e;
+    frexp(m, &e);                        // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(1-e) in [1, 2)
+    sc = ldexp(1.0, 1 - e);
+  }
+  scale[i] = sc;
+}
+
+__global__ void __launch_bounds__(256) row_scale_kernel(double *A, long long rows, long long cols, long long ld,
+                                                        const double *scale) {
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const double sc = scale[r];
+  if (sc == 1.0) return;
+  const int lane = threadIdx.x & 31;
+  double *row = A + r * ld;
+  const long long c2 = cols & ~1LL;
+  for (long long c = 2LL * lane; c < c2; c += 64) {
+    double2 v = *reinterpret_cast<double2 *>(row + c);
+    v.x *= sc; v.y *= sc;
+    *reinterpret_cast<double2 *>(row + c) = v;
+  }
+  if (lane == 0 && c2 < cols) row[c2] *= sc;
+}
+
+int row_absmax(const double *A, int64_t rows, int64_t cols, int64_t ld, double *out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  row_absmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A, rows, cols, ld, out);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+int scale_from_absmax(const double *absmax, int64_t n, double *scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  scale_from_absmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(absmax, n, scale);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+int row_scale(double *A, int64_t rows, int64_t cols, int64_t ld, const double *scale, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  row_scale_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(A, rows, cols, ld, scale);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- pivots -> permutation ------------------------------------------------------------------------
 // perm[i] = index of the original row that the interchanges leave at position i.
 __global__ void perm_init_kernel(int32_t *perm, int n) {

@@ -68,6 +68,8 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   const size_t nflags = (size_t)((n + 127) / 128) + 1;
   if (e == cudaSuccess) e = cudaMalloc(&h->sweep_flags, sizeof(unsigned int) * nflags);
   if (e == cudaSuccess) e = cudaMemset(h->sweep_flags, 0, sizeof(unsigned int) * nflags);
+  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->sweep_ticket, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&h->sweep_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->sweep_err, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
@@ -83,7 +85,7 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
 extern "C" int updes_lu_destroy(UpdesLU *h) {
   if (!h) return 0;
   cudaFree(h->cand); cudaFree(h->top); cudaFree(h->candval); cudaFree(h->candrow);
-  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters); cudaFree(h->sweep_flags); cudaFree(h->sweep_err);
+  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters); cudaFree(h->sweep_flags); cudaFree(h->sweep_err); cudaFree(h->sweep_ticket);
   delete h;
   return 0;
 }
@@ -93,19 +95,82 @@ extern "C" int updes_lu_bind(UpdesLU *h, int slot, double *ptr, int64_t rows, in
   return updes::lu_bind_view(h, slot, ptr, rows, ld);
 }
 
-extern "C" int updes_lu_factor(UpdesLU *h, double *K, int32_t *ipiv, int32_t *info, void *stream) {
+static int lu_factor_impl(UpdesLU *h, double *K, int32_t *ipiv, double *scale, int32_t *info, cudaStream_t st) {
   if (!h) return -1;
   if (!K || (((uintptr_t)K) & 127)) return -2;   // rows must be whole 128-byte lines
   if (!ipiv) return -3;
-  if (!info) return -4;
+  if (!info) return -5;
   if (h->ld < h->n) return -1;
-  cudaStream_t st = (cudaStream_t)stream;
   UPDES_CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
   int rc = updes::lu_bind_view(h, 0, K, h->n, h->ld);
   if (rc) return rc;
+  h->row_scale = nullptr;
+  if (scale) {
+    // row equilibration: scale[] doubles as the scratch for the row maxima
+    rc = updes::row_absmax(K, h->n, h->n, h->ld, scale, st);
+    if (rc) return rc;
+    rc = updes::scale_from_absmax(scale, h->n, scale, st);
+    if (rc) return rc;
+    rc = updes::row_scale(K, h->n, h->n, h->ld, scale, st);
+    if (rc) return rc;
+    h->row_scale = scale;
+  }
   rc = updes::lu_recursive(h, 0, 0, 0, h->n, 0, h->n, ipiv, info, st);
   if (rc) return rc;
   return updes::build_permutation(h, ipiv, st);
+}
+
+extern "C" int updes_lu_factor(UpdesLU *h, double *K, int32_t *ipiv, int32_t *info, void *stream) {
+  int rc = lu_factor_impl(h, K, ipiv, nullptr, info, (cudaStream_t)stream);
+  return rc == -5 ? -4 : rc;
+}
+
+extern "C" int updes_lu_factor_scaled(UpdesLU *h, double *K, int32_t *ipiv, double *scale, int32_t *info, void *stream) {
+  if (!scale) return -4;
+  return lu_factor_impl(h, K, ipiv, scale, info, (cudaStream_t)stream);
+}
+
+extern "C" int updes_lu_set_row_scale(UpdesLU *h, const double *scale) {
+  if (!h) return -1;
+  h->row_scale = scale;
+  return 0;
+}
+
+extern "C" int updes_row_absmax(const double *A, int64_t rows, int64_t cols, int64_t ld, double *out, void *stream) {
+  if (!A) return -1;
+  if (rows < 0) return -2;
+  if (cols < 0 || cols > ld) return -3;
+  if (ld & 1) return -4;
+  if (!out) return -5;
+  return updes::row_absmax(A, rows, cols, ld, out, (cudaStream_t)stream);
+}
+
+extern "C" int updes_scale_from_absmax(const double *absmax, int64_t n, double *scale, void *stream) {
+  if (!absmax) return -1;
+  if (n < 0) return -2;
+  if (!scale) return -3;
+  return updes::scale_from_absmax(absmax, n, scale, (cudaStream_t)stream);
+}
+
+extern "C" int updes_row_scale(double *A, int64_t rows, int64_t cols, int64_t ld, const double *scale, void *stream) {
+  if (!A) return -1;
+  if (rows < 0) return -2;
+  if (cols < 0 || cols > ld) return -3;
+  if (ld & 1) return -4;
+  if (!scale) return -5;
+  return updes::row_scale(A, rows, cols, ld, scale, (cudaStream_t)stream);
+}
+
+/* Internal-failure flags of the handle's kernels, read back synchronously on `stream`: bit 0 = a wait inside a
+ * triangular sweep timed out.  (A timed-out grid barrier of the panel kernel is reported as info = -1.) */
+extern "C" int updes_lu_status(UpdesLU *h, int32_t *host_flags, void *stream) {
+  if (!h) return -1;
+  if (!host_flags) return -2;
+  int v = 0;
+  UPDES_CUDA_TRY(cudaMemcpyAsync(&v, h->sweep_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  UPDES_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *host_flags = v;
+  return 0;
 }
 
 extern "C" int updes_lu_panel(UpdesLU *h, double *K, int64_t r0, int64_t nc, int32_t *ipiv, int32_t *info,

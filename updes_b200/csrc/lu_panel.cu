@@ -401,12 +401,360 @@ __global__ void __launch_bounds__(CLUSTER_PANEL_THREADS, 1) lu_panel_cluster_ker
   cluster.sync();   // nobody may exit while a peer can still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second-generation panel kernels (panel_variant 2, default).  Same arithmetic and the same pivots as
+// the kernels above; what changes is the per-column latency chain:
+//   * implicit pivoting: rows never move during the panel.  Each row carries its current logical
+//     position; an interchange is two threads updating an integer, and the rows are written to their
+//     final positions once, at the end.  (The diagonal row no longer has to be published per column.)
+//   * arg-max on the integer pipe: |a| is compared as a 64-bit pattern with three REDUX instructions
+//     (max of the high words, max of the low words among those, min position among the maxima: LAPACK's
+//     first-index tie-break) instead of five shuffle rounds on (value, row) pairs, and every warp reduces
+//     the per-warp candidates redundantly, so there is one block barrier per column, not two;
+//   * cluster kernel: every CTA PUSHES its candidate (key, position, the whole row) into the shared
+//     memory of all CTAs of the cluster, then one split cluster barrier (arrive.release / wait.acquire);
+//     after the barrier everything a CTA needs is in its own shared memory -- no dependent remote reads;
+//   * grid kernel: the thread that owns the CTA's candidate publishes it and arrives at the grid barrier
+//     itself (no block barrier between publish and arrive).
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned int FULL = 0xffffffffu;
+constexpr int NOPOS = 0x7fffffff;
+
+__device__ __forceinline__ unsigned long long abs_key(double v) {
+  const double av = fabs(v);
+  return av == av ? (unsigned long long)__double_as_longlong(av) : 0ull;    // NaN never wins a comparison
+}
+
+// warp-wide arg-max of (key, pos): largest key, ties -> smallest pos.  All lanes get the result.
+__device__ __forceinline__ void warp_argmax(unsigned long long &key, int &pos) {
+  const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+  const unsigned int mhi = __reduce_max_sync(FULL, hi);
+  const unsigned int mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+  const bool match = hi == mhi && lo == mlo;
+  const unsigned int mp = __reduce_min_sync(FULL, match ? (unsigned int)pos : (unsigned int)NOPOS);
+  key = ((unsigned long long)mhi << 32) | mlo;
+  pos = (int)mp;
+}
+
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int JB>
+__global__ void __launch_bounds__(CLUSTER_PANEL_THREADS, 1) lu_panel_cluster2_kernel(PanelParams P) {
+  constexpr int MAXC = 16;
+  __shared__ unsigned long long s_key[2][32];
+  __shared__ int s_pos[2][32];
+  __shared__ __align__(16) double s_stage[2][JB];
+  __shared__ __align__(16) double x_cand[2][MAXC][JB];          // pushed by the CTAs of the cluster
+  __shared__ __align__(16) unsigned long long x_kp[2][MAXC][2]; // (key, position) of each CTA's candidate
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int b = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+  const int jb = P.jb;
+  const long long row = P.r0 + (long long)b * P.rows_per_cta + tid;
+  const bool valid = tid < P.rows_per_cta && row < P.n;
+  int mypos = valid ? (int)row : NOPOS;       // current logical position of my row
+  bool active = valid;                        // not yet chosen as a pivot row
+
+  double a[JB];
+  if (valid) {
+    const double *src = P.K + row * P.ld + P.c0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + c);
+        a[c] = v.x; a[c + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++) a[c] = c < jb ? src[c] : 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < JB; c++) a[c] = 0.0;
+  }
+
+#pragma unroll 1
+  for (int g = 0; g < JB / 8; g++) {           // 8 unrolled column steps per group, rows rotated by 8 in between
+  const int live = JB - 8 * g;
+#pragma unroll
+  for (int jl = 0; jl < 8; jl++) {
+    const int j = 8 * g + jl;
+    if (j < jb) {   // uniform
+      const int diag = (int)P.r0 + j;
+      const int par = j & 1;
+      // ---- candidate of this CTA (every warp ends up knowing it) ------------------------------------
+      unsigned long long key = active ? abs_key(a[jl]) : 0ull;
+      int pos = active ? mypos : NOPOS;
+      warp_argmax(key, pos);
+      if (lane == 0) { s_key[par][warp] = key; s_pos[par][warp] = pos; }
+      __syncthreads();
+      unsigned long long ckey = lane < nwarps ? s_key[par][lane] : 0ull;
+      int cpos = lane < nwarps ? s_pos[par][lane] : NOPOS;
+      warp_argmax(ckey, cpos);
+      // ---- push it to every CTA of the cluster -----------------------------------------------------------
+      const unsigned int own = __ballot_sync(FULL, active && mypos == cpos);
+      if (own) {                                // this warp holds the candidate row
+        if (lane == __ffs(own) - 1) {
+#pragma unroll
+          for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(&s_stage[par][c]) = make_double2(a[c], a[c + 1]);
+        }
+        __syncwarp();
+        constexpr int CH = JB / 2;              // 16-byte chunks per row
+        const int chunk = lane % CH;
+        const double2 v = *reinterpret_cast<const double2 *>(&s_stage[par][2 * chunk]);
+        for (int d = lane / CH; d < C; d += 32 / CH) {
+          double *remote = cluster.map_shared_rank(&x_cand[par][b][0], d);
+          *reinterpret_cast<double2 *>(remote + 2 * chunk) = v;
+        }
+      }
+      if (warp == 0 && lane < C) {
+        unsigned long long *remote = cluster.map_shared_rank(&x_kp[par][b][0], lane);
+        *reinterpret_cast<ulonglong2 *>(remote) = make_ulonglong2(ckey, (unsigned long long)(unsigned int)cpos);
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      // ---- winner: everything is in local shared memory now ------------------------------------------------
+      unsigned long long wkey = 0ull;
+      int wpos = NOPOS;
+      if (lane < C) {
+        const ulonglong2 kp = *reinterpret_cast<const ulonglong2 *>(&x_kp[par][lane][0]);
+        wkey = kp.x; wpos = (int)(unsigned int)kp.y;
+      }
+      const int lpos = wpos;
+      warp_argmax(wkey, wpos);
+      const int wb = (int)__reduce_min_sync(FULL, (lane < C && lpos == wpos) ? (unsigned int)lane : 99u);
+      const double *prow = &x_cand[par][wb][0];
+      if (b == 0 && tid == 0) {
+        P.ipiv[diag] = wpos;
+        if (wkey == 0ull) atomicCAS(P.info, 0, diag + 1);
+      }
+      // ---- interchange (positions only) + rank-1 update -------------------------------------------------------
+      const double pval = prow[jl];
+      const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
+      if (active) {
+        if (mypos == wpos) {
+          active = false; mypos = diag;                      // pivot row: frozen, will land on the diagonal
+        } else {
+          if (mypos == diag) mypos = wpos;                   // displaced by the interchange
+          if (pval != 0.0) {
+            const double l = a[jl] * rinv;
+            a[jl] = l;
+#pragma unroll
+            for (int c = jl + 1; c < JB; c++)
+              if (c < live) a[c] = fma(-l, prow[c], a[c]);
+          }
+        }
+      }
+    }
+  }
+  {
+    double t8[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) t8[c] = a[c];
+#pragma unroll
+    for (int c = 0; c < JB - 8; c++) a[c] = a[c + 8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[JB - 8 + c] = t8[c];
+  }
+  }
+  if (valid) {
+    double *dst = P.K + (long long)mypos * P.ld + P.c0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(a[c], a[c + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++)
+        if (c < jb) dst[c] = a[c];
+    }
+  }
+  // no trailing cluster barrier needed: a CTA leaves the last column's barrier only after every CTA has
+  // arrived there, i.e. after the last remote store into its shared memory was issued and released
+}
+
+// Grid-wide variant: candidates through global memory, one grid barrier per column.
+template <int JB, int RPT>
+__global__ void __launch_bounds__(PANEL_THREADS, 1) lu_panel2_kernel(PanelParams P) {
+  __shared__ unsigned long long s_key[2][32];
+  __shared__ int s_pos[2][32];
+  __shared__ __align__(16) double s_prow[JB];
+  __shared__ int s_piv;
+
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int b = blockIdx.x;
+  const int jb = P.jb;
+  const long long cta_row0 = P.r0 + (long long)b * P.rows_per_cta;
+
+  double a[RPT][JB];
+  int mypos[RPT];
+  bool active[RPT];
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    const int li = tid + q * T;
+    const long long row = cta_row0 + li;
+    const bool valid = li < P.rows_per_cta && row < P.n;
+    mypos[q] = valid ? (int)row : NOPOS;
+    active[q] = valid;
+    if (valid) {
+      const double *src = P.K + row * P.ld + P.c0;
+      if (jb == JB) {
+#pragma unroll
+        for (int c = 0; c < JB; c += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(src + c);
+          a[q][c] = v.x; a[q][c + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < JB; c++) a[q][c] = c < jb ? src[c] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++) a[q][c] = 0.0;
+    }
+  }
+  const bool valid0 = mypos[0] != NOPOS;      // RPT > 1: validity per slot is re-derived at the store
+
+  unsigned int target = P.barrier_base;
+  unsigned long long *candkey = reinterpret_cast<unsigned long long *>(P.candval);
+
+#pragma unroll 1
+  for (int g = 0; g < JB / 8; g++) {
+  const int live = JB - 8 * g;
+#pragma unroll
+  for (int jl = 0; jl < 8; jl++) {
+    const int j = 8 * g + jl;
+    if (j < jb) {   // uniform
+      const int diag = (int)P.r0 + j;
+      const int par = j & 1;
+      // ---- candidate of this CTA ------------------------------------------------------------------
+      unsigned long long key = 0ull;
+      int pos = NOPOS;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (active[q]) {
+          const unsigned long long k = abs_key(a[q][jl]);
+          if (k > key || (k == key && mypos[q] < pos)) { key = k; pos = mypos[q]; }
+        }
+      }
+      warp_argmax(key, pos);
+      if (lane == 0) { s_key[par][warp] = key; s_pos[par][warp] = pos; }
+      __syncthreads();
+      unsigned long long ckey = lane < nwarps ? s_key[par][lane] : 0ull;
+      int cpos = lane < nwarps ? s_pos[par][lane] : NOPOS;
+      warp_argmax(ckey, cpos);
+      // ---- publish + arrive: done by the one thread that owns the candidate row ---------------------------
+      target += (unsigned int)P.num_ctas;
+      bool arrive = (cpos == NOPOS) && tid == 0;             // a CTA without active rows still has to arrive
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (active[q] && mypos[q] == cpos) {
+          double *dst = P.cand + ((size_t)par * P.num_ctas + b) * JB;
+#pragma unroll
+          for (int c = 0; c < JB; c += 2) __stcg(reinterpret_cast<double2 *>(dst + c), make_double2(a[q][c], a[q][c + 1]));
+          arrive = true;
+        }
+      }
+      if (arrive) {
+        __stcg(candkey + par * P.num_ctas + b, ckey);
+        __stcg(P.candrow + par * P.num_ctas + b, cpos);
+        __threadfence();
+        atomicAdd(P.barrier, 1u);
+      }
+      if (tid == 0) {
+        // bounded spin: a lost arrival must not hang the device (info = -1 flags the failure)
+        unsigned int polls = 0;
+        while ((int)(ld_acquire_u32(P.barrier) - target) < 0) {
+          if (++polls > (1u << 24)) { atomicExch(P.info, -1); break; }
+        }
+      }
+      __syncthreads();
+      // ---- winner ------------------------------------------------------------------------------------
+      if (warp == 0) {
+        unsigned long long wkey = 0ull;
+        int wpos = NOPOS, wb = 0;
+        constexpr int PER = 5;                                 // up to 160 CTAs
+        unsigned long long k5[PER];
+        int p5[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+          const int c = lane + 32 * u;
+          const bool in = c < P.num_ctas;
+          k5[u] = in ? __ldcg(candkey + par * P.num_ctas + c) : 0ull;
+          p5[u] = in ? __ldcg(P.candrow + par * P.num_ctas + c) : NOPOS;
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+          if (k5[u] > wkey || (k5[u] == wkey && p5[u] < wpos)) { wkey = k5[u]; wpos = p5[u]; wb = lane + 32 * u; }
+        const int lpos = wpos;
+        warp_argmax(wkey, wpos);
+        wb = (int)__reduce_min_sync(FULL, (lpos == wpos && wpos != NOPOS) ? (unsigned int)wb : 0xffffu);
+        if (wb == 0xffff) wb = 0;
+        if (lane < JB) s_prow[lane] = __ldcg(P.cand + ((size_t)par * P.num_ctas + wb) * JB + lane);
+        if (lane == 0) {
+          s_piv = wpos;
+          if (b == 0) {
+            P.ipiv[diag] = wpos;
+            if (wkey == 0ull) atomicCAS(P.info, 0, diag + 1);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- interchange (positions only) + rank-1 update ------------------------------------------------------------
+      const int wpos = s_piv;
+      const double pval = s_prow[jl];
+      const double rinv = pval != 0.0 ? 1.0 / pval : 0.0;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        if (!active[q]) continue;
+        if (mypos[q] == wpos) { active[q] = false; mypos[q] = diag; continue; }
+        if (mypos[q] == diag) mypos[q] = wpos;
+        if (pval != 0.0) {
+          const double l = a[q][jl] * rinv;
+          a[q][jl] = l;
+#pragma unroll
+          for (int c = jl + 1; c < JB; c++)
+            if (c < live) a[q][c] = fma(-l, s_prow[c], a[q][c]);
+        }
+      }
+    }
+  }
+  // rotate the register rows left by 8 columns
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    double t8[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) t8[c] = a[q][c];
+#pragma unroll
+    for (int c = 0; c < JB - 8; c++) a[q][c] = a[q][c + 8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[q][JB - 8 + c] = t8[c];
+  }
+  }
+  (void)valid0;
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    if (mypos[q] == NOPOS) continue;
+    double *dst = P.K + (long long)mypos[q] * P.ld + P.c0;
+    if (jb == JB) {
+#pragma unroll
+      for (int c = 0; c < JB; c += 2) *reinterpret_cast<double2 *>(dst + c) = make_double2(a[q][c], a[q][c + 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < JB; c++)
+        if (c < jb) dst[c] = a[q][c];
+    }
+  }
+}
+
 // largest cluster size (<= 16) this device can co-schedule for the cluster panel kernel; 0 = unsupported
-static int cluster_panel_max(UpdesLU *h) {
-  static int cached = -1;
+typedef void (*PanelKernelFn)(PanelParams);
+
+static int cluster_panel_max_for(PanelKernelFn fn, int &cached) {
   if (cached >= 0) return cached;
   cached = 0;
-  if (cudaFuncSetAttribute(lu_panel_cluster_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
     cudaGetLastError();
   }
   for (int c = 16; c >= 1; c >>= 1) {
@@ -417,14 +765,19 @@ static int cluster_panel_max(UpdesLU *h) {
     at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, lu_panel_cluster_kernel<32>, &cfg) == cudaSuccess && nclusters >= 1) {
+    if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) == cudaSuccess && nclusters >= 1) {
       cached = c;
       break;
     }
     cudaGetLastError();
   }
-  (void)h;
   return cached;
+}
+
+static int cluster_panel_max(UpdesLU *h) {
+  static int cached1 = -1, cached2 = -1;
+  return h->panel_variant == 2 ? cluster_panel_max_for(lu_panel_cluster2_kernel<32>, cached2)
+                               : cluster_panel_max_for(lu_panel_cluster_kernel<32>, cached1);
 }
 
 static int launch_panel_cluster(UpdesLU *h, PanelParams &P, int ctas, int threads, cudaStream_t st) {
@@ -435,11 +788,11 @@ static int launch_panel_cluster(UpdesLU *h, PanelParams &P, int ctas, int thread
   at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   prof_begin(PROF_PANEL, (double)(P.n - P.r0) * P.jb * P.jb, st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<32>, P);
+  cudaError_t e = h->panel_variant == 2 ? cudaLaunchKernelEx(&cfg, lu_panel_cluster2_kernel<32>, P)
+                                        : cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<32>, P);
   prof_end(st);
   if (e != cudaSuccess) return (int)e;
   ++g_launch_count;
-  (void)h;
   return 0;
 }
 
@@ -447,8 +800,8 @@ template <int JB, int RPT>
 static int launch_panel(UpdesLU *h, PanelParams &P, int threads, cudaStream_t st) {
   void *args[] = {&P};
   prof_begin(PROF_PANEL, (double)(P.n - P.r0) * P.jb * P.jb, st);
-  cudaError_t le = cudaLaunchCooperativeKernel((void *)lu_panel_kernel<JB, RPT>, dim3(P.num_ctas), dim3(threads), args,
-                                               0, st);
+  void *fn = h->panel_variant == 2 ? (void *)lu_panel2_kernel<JB, RPT> : (void *)lu_panel_kernel<JB, RPT>;
+  cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(P.num_ctas), dim3(threads), args, 0, st);
   prof_end(st);
   if (le != cudaSuccess) return (int)le;
   ++g_launch_count;
@@ -474,7 +827,7 @@ int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ip
   if (JBmax == 0) return -3;
   if (jb > JBmax) return -4;
   // short panels: one thread-block cluster, DSMEM exchange, hardware cluster barrier
-  if (h->panel_variant == 1 && JBmax == 32) {
+  if (h->panel_variant >= 1 && JBmax == 32) {
     const int cmax = cluster_panel_max(h);
     if (cmax > 0 && m <= (int64_t)cmax * CLUSTER_PANEL_THREADS) {
       int c = 1;

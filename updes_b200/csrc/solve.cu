@@ -21,12 +21,14 @@ namespace updes {
 constexpr int SB = 128;
 constexpr int SOLVE_MAX_RHS = 4;
 
+// X = P (diag(scale) B): row equilibration factors (if any) are applied while gathering
 __global__ void gather_rows_kernel(const double *B, long long ldb, int nrhs, const int32_t *perm, long long n,
-                                   double *X) {
+                                   double *X, const double *scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int p = perm[i];
-  for (int f = 0; f < nrhs; f++) X[f * n + i] = B[f * ldb + p];
+  const double sc = scale ? scale[p] : 1.0;
+  for (int f = 0; f < nrhs; f++) X[f * n + i] = B[f * ldb + p] * sc;
 }
 
 __global__ void copy_back_kernel(double *B, long long ldb, int nrhs, long long n, const double *X) {
@@ -259,11 +261,14 @@ tri_step_t_kernel(const double *LU, long long ld, long long n, long long k0, int
   }
 }
 
-__global__ void scatter_rows_kernel(const double *Z, long long n, int nrhs, const int32_t *perm, double *B, long long ldb) {
+// with row equilibration  P diag(s) K = L U,  K^T = U^T L^T P diag(s)^-1,  so  x = diag(s) P^T z
+__global__ void scatter_rows_kernel(const double *Z, long long n, int nrhs, const int32_t *perm, double *B, long long ldb,
+                                    const double *scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int p = perm[i];
-  for (int f = 0; f < nrhs; f++) B[f * ldb + p] = Z[f * n + i];
+  const double sc = scale ? scale[p] : 1.0;
+  for (int f = 0; f < nrhs; f++) B[f * ldb + p] = Z[f * n + i] * sc;
 }
 
 __global__ void copy_in_kernel(const double *B, long long ldb, int nrhs, long long n, double *X) {
@@ -544,6 +549,310 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) tri_sweep_kernel(SweepParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-block streaming sweep (default, solve_variant 2): ONE launch per sweep direction.
+//
+// The step-synchronous kernel above makes every CTA wait for block step kb before touching any of its
+// tiles of that step; its serial chain (flag -> update -> substitution -> publish, ~6.5 us per 128-row
+// block) therefore gates ALL traffic and the sweep ran at 52 % of HBM.  Here the work is cut the other
+// way: a CTA takes one 128-row block j at a time (dynamic ticket, handed out in dependency order) and
+// streams that block's row panel -- tiles (j, kb) for every block step kb before it -- accumulating
+// X[j] - sum_kb L[j,kb] x_kb in registers.  Only the LAST tile of a block is on the critical path; all
+// earlier ones have slack, so while one CTA at a time finishes "its" diagonal solve, the other ~147
+// keep streaming L / U at HBM rate.  No block step ever waits for stragglers.
+//   * solved blocks are published through the data itself: Y is pre-filled with a signalling-NaN
+//     sentinel, the solver overwrites it, consumers (one warp per CTA) poll the 1 KB they need and
+//     re-broadcast it through shared memory -- one L2 round trip, no flag, no fence on the chain;
+//   * deadlock-free without co-residency: tickets are taken in dependency order by running CTAs, so
+//     every block a CTA waits for is held by a CTA that is already executing;
+//   * the diagonal tile is staged in shared memory when the block starts (long before its turn), the
+//     32x32 triangular sub-solves keep one row per lane in registers: plain substitution, no inverses.
+// The same kernel serves the multi-GPU path: block steps restricted to [kb_begin, kb_end) (the column
+// block this rank owns); row blocks past kb_end only get their X updated.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW2_THREADS = 512;
+constexpr int SW2_NW = SW2_THREADS / 32;
+constexpr int SW2_RW = SB / SW2_NW;            // rows per warp (8)
+constexpr unsigned long long SW2_SENTINEL = 0x7FF4DEADBEEF5EEDull;   // signalling NaN never produced by arithmetic
+
+template <int NR>
+struct Sw2Smem {
+  double T[SB * (SB + 1)];
+  double xs[NR][SB];            // right-hand side / solution of the diagonal block being solved
+  double sx[2][NR][SB];         // x_kb of the tile in flight (double-buffered)
+  int ticket;
+};
+
+struct Sweep2Params {
+  const double *LU;
+  long long ld, n;
+  long long cbase;              // column of diagonal block kb = cbase + 128 kb
+  int kb_begin, kb_end;         // block steps available in this factor
+  int nblk;                     // ceil(n / 128)
+  double *X, *Y;
+  unsigned int *ticket;         // dynamic row-block counter (monotonic across launches)
+  unsigned int ticket_base;
+  int *err;
+};
+
+__device__ __forceinline__ double2 ld_relaxed_f64x2(const double *p) {
+  double2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == SW2_SENTINEL; }
+
+__global__ void fill_sentinel_kernel(double *Y, long long n, long long r0, long long cnt, int nrhs) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= cnt * nrhs) return;
+  const long long f = t / cnt, c = t % cnt;
+  Y[f * n + r0 + c] = __longlong_as_double((long long)SW2_SENTINEL);
+}
+
+template <bool UPPER, int NR>
+__global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params P) {
+  extern __shared__ __align__(16) unsigned char sw2_raw[];
+  Sw2Smem<NR> &S = *reinterpret_cast<Sw2Smem<NR> *>(sw2_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nsteps = P.kb_end - P.kb_begin;
+  const int nrowblocks = UPPER ? P.kb_end : P.nblk - P.kb_begin;
+  const long long n = P.n;
+
+  while (true) {
+    __syncthreads();                                       // previous block's shared state is dead
+    if (tid == 0) S.ticket = (int)(atomicAdd(P.ticket, 1u) - P.ticket_base);
+    __syncthreads();
+    const int i = S.ticket;                                // order index of my row block
+    if (i >= nrowblocks) break;
+    const int j = UPPER ? P.kb_end - 1 - i : P.kb_begin + i;
+    const bool diag = i < nsteps;
+    const int ntiles = diag ? i : nsteps;
+    const long long r0 = 128LL * j;
+    const int nbj = (int)min(128LL, n - r0);
+
+    if (diag) {                                            // stage the diagonal tile: off the critical path
+      const double *base = P.LU + r0 * P.ld + P.cbase + r0;
+      if (nbj == SB) {
+#pragma unroll
+        for (int g = 0; g < SB / SW2_NW; g += 4) {
+          double v[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[u][q] = base[(long long)(warp + (g + u) * SW2_NW) * P.ld + lane + 32 * q];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) S.T[(warp + (g + u) * SW2_NW) * (SB + 1) + lane + 32 * q] = v[u][q];
+        }
+      } else {
+        for (int r = warp; r < SB; r += SW2_NW)
+          for (int c = lane; c < SB; c += 32)
+            S.T[r * (SB + 1) + c] = (r < nbj && c < nbj) ? base[(long long)r * P.ld + c] : (r == c ? 1.0 : 0.0);
+      }
+    }
+
+    // ---- stream the row panel: acc[u][f] = partial sums of row (warp + u*NW) over my 4 columns per tile ----
+    double acc[SW2_RW][NR];
+#pragma unroll
+    for (int u = 0; u < SW2_RW; u++)
+#pragma unroll
+      for (int f = 0; f < NR; f++) acc[u][f] = 0.0;
+
+    for (int t = 0; t < ntiles; t++) {
+      const int kb = UPPER ? P.kb_end - 1 - t : P.kb_begin + t;
+      const long long k0 = 128LL * kb;
+      const int nb = (int)min(128LL, n - k0);
+      const double *tile = P.LU + r0 * P.ld + P.cbase + k0;
+      // NR == 1: the whole tile (8 rows per warp) is issued before waiting for x_kb; with 4 right-hand sides
+      // the accumulators take the registers, so the tile goes through in two halves of 4 rows per warp
+      constexpr int HR = NR == 1 ? SW2_RW : SW2_RW / 2;
+      double2 v0[HR], v1[HR];
+      auto load_rows = [&](int ubase) {
+        if (nb == SB && nbj == SB) {
+#pragma unroll
+          for (int u = 0; u < HR; u++) {
+            const double *row = tile + (long long)(warp + (ubase + u) * SW2_NW) * P.ld;
+            v0[u] = *reinterpret_cast<const double2 *>(row + 2 * lane);
+            v1[u] = *reinterpret_cast<const double2 *>(row + 64 + 2 * lane);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < HR; u++) {
+            const int r = warp + (ubase + u) * SW2_NW;
+            const double *row = tile + (long long)r * P.ld;
+            const bool rv = r < nbj;
+            v0[u].x = (rv && 2 * lane < nb) ? row[2 * lane] : 0.0;
+            v0[u].y = (rv && 2 * lane + 1 < nb) ? row[2 * lane + 1] : 0.0;
+            v1[u].x = (rv && 64 + 2 * lane < nb) ? row[64 + 2 * lane] : 0.0;
+            v1[u].y = (rv && 65 + 2 * lane < nb) ? row[65 + 2 * lane] : 0.0;
+          }
+        }
+      };
+      load_rows(0);
+      // x_kb: warp 0 polls the published block (sentinel = not solved yet) and re-broadcasts it
+      double (*sx)[SB] = S.sx[t & 1];
+      if (warp == 0) {
+        unsigned int polls = 0;
+#pragma unroll
+        for (int f = 0; f < NR; f++) {
+          const double *yb = P.Y + (long long)f * n + k0;
+          double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+          while (true) {
+            bool ok = true;
+            if (nb == SB) {
+              a = ld_relaxed_f64x2(yb + 2 * lane);
+              b = ld_relaxed_f64x2(yb + 64 + 2 * lane);
+              ok = !(is_sentinel(a.x) || is_sentinel(a.y) || is_sentinel(b.x) || is_sentinel(b.y));
+            } else {
+              volatile const double *yv = yb;
+              a.x = 2 * lane < nb ? yv[2 * lane] : 0.0;
+              a.y = 2 * lane + 1 < nb ? yv[2 * lane + 1] : 0.0;
+              b.x = 64 + 2 * lane < nb ? yv[64 + 2 * lane] : 0.0;
+              b.y = 65 + 2 * lane < nb ? yv[65 + 2 * lane] : 0.0;
+              ok = !(is_sentinel(a.x) || is_sentinel(a.y) || is_sentinel(b.x) || is_sentinel(b.y));
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++polls > (1u << 22)) { if (lane == 0) atomicExch(P.err, 1); break; }   // never expected
+          }
+          *reinterpret_cast<double2 *>(&sx[f][2 * lane]) = a;
+          *reinterpret_cast<double2 *>(&sx[f][64 + 2 * lane]) = b;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int half = 0; half < SW2_RW / HR; half++) {
+        if (half > 0) load_rows(half * HR);
+#pragma unroll
+        for (int f = 0; f < NR; f++) {
+          const double2 xa = *reinterpret_cast<const double2 *>(&sx[f][2 * lane]);
+          const double2 xb = *reinterpret_cast<const double2 *>(&sx[f][64 + 2 * lane]);
+#pragma unroll
+          for (int u = 0; u < HR; u++)
+            acc[half * HR + u][f] = fma(v1[u].y, xb.y, fma(v1[u].x, xb.x, fma(v0[u].y, xa.y, fma(v0[u].x, xa.x, acc[half * HR + u][f]))));
+        }
+      }
+    }
+
+    // ---- reduce across lanes: lane u (< RW) ends up with the sum of row warp + u*NW ----------------------
+#pragma unroll
+    for (int f = 0; f < NR; f++) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int u = 0; u < SW2_RW; u++) acc[u][f] += __shfl_xor_sync(0xffffffffu, acc[u][f], off);
+      if (lane < SW2_RW) {
+        double mine = acc[0][f];
+#pragma unroll
+        for (int u = 1; u < SW2_RW; u++) mine = lane == u ? acc[u][f] : mine;
+        const int r = warp + lane * SW2_NW;
+        if (r < nbj) {
+          double *xp = P.X + (long long)f * n + r0 + r;
+          if (diag) S.xs[f][r] = *xp - mine;
+          else *xp -= mine;
+        } else if (diag) {
+          S.xs[f][r] = 0.0;
+        }
+      }
+    }
+    if (!diag) continue;
+    __syncthreads();
+
+    // ---- triangular solve of the diagonal block (substitution, 32x32 sub-blocks in registers) ------------
+    for (int q = 0; q < 4; q++) {
+      const int sb = UPPER ? 3 - q : q;
+      const int base = sb * 32;
+      if (warp == 0) {
+        double trow[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) trow[c] = S.T[(base + lane) * (SB + 1) + base + c];
+        double rd = 1.0;
+        if (UPPER) {
+          double d = trow[0];
+#pragma unroll
+          for (int c = 1; c < 32; c++) d = lane == c ? trow[c] : d;
+          rd = 1.0 / d;
+        }
+#pragma unroll
+        for (int f = 0; f < NR; f++) {
+          double x = S.xs[f][base + lane];
+          if (!UPPER) {
+#pragma unroll
+            for (int c = 0; c < 31; c++) {
+              const double xc = __shfl_sync(0xffffffffu, x, c);
+              if (lane > c) x = fma(-trow[c], xc, x);
+            }
+          } else {
+#pragma unroll
+            for (int c = 31; c >= 0; c--) {
+              if (lane == c) x *= rd;
+              const double xc = __shfl_sync(0xffffffffu, x, c);
+              if (lane < c) x = fma(-trow[c], xc, x);
+            }
+          }
+          S.xs[f][base + lane] = x;
+          // publish this sub-block at once: consumers poll the data itself
+          if (base + lane < nbj) __stcg(P.Y + (long long)f * n + r0 + base + lane, x);
+        }
+      }
+      __syncthreads();
+      if (q == 3) break;
+      // remaining sub-blocks of this diagonal block: 4 threads per row, 8 columns each
+      const int rbeg = UPPER ? 0 : base + 32, rend = UPPER ? base : SB;
+      const int nrow = rend - rbeg;
+      for (int t = tid; t < nrow * 4 * NR; t += SW2_THREADS) {
+        const int part = t & 3, rr = (t >> 2) % nrow, f = (t >> 2) / nrow;
+        const int r = rbeg + rr;
+        const double *trow = S.T + r * (SB + 1) + base + part * 8;
+        const double *xv = &S.xs[f][base + part * 8];
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) v = fma(trow[c], xv[c], v);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (part == 0) S.xs[f][r] -= v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <bool UPPER, int NR>
+static int launch_sweep2(UpdesLU *h, Sweep2Params &P, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    UPDES_CUDA_TRY(cudaFuncSetAttribute(tri_sweep2_kernel<UPPER, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(Sw2Smem<NR>)));
+    attr = true;
+  }
+  tri_sweep2_kernel<UPPER, NR><<<grid, SW2_THREADS, sizeof(Sw2Smem<NR>), st>>>(P);
+  UPDES_LAUNCH_CHECK();
+  (void)h;
+  return 0;
+}
+
+// Block steps [kb_begin, kb_end) of the factor stored at `LU` (diagonal block kb at column cbase + 128 kb).
+// X is the running right-hand side (rows past the solved range are updated in place), Y receives the
+// solved blocks.  nrhs <= SOLVE_MAX_RHS.
+int tri_sweep_rowblock(UpdesLU *h, const double *LU, long long ld, long long n, bool upper, long long cbase,
+                       int kb_begin, int kb_end, double *X, double *Y, int nrhs, cudaStream_t st) {
+  if (kb_end <= kb_begin) return 0;
+  const int nblk = (int)((n + SB - 1) / SB);
+  const long long y0 = 128LL * kb_begin;
+  const long long ycnt = (128LL * kb_end < n ? 128LL * kb_end : n) - y0;
+  const int nr = nrhs > 1 ? SOLVE_MAX_RHS : 1;
+  fill_sentinel_kernel<<<(unsigned)((ycnt * nr + 255) / 256), 256, 0, st>>>(Y, n, y0, ycnt, nr);
+  UPDES_LAUNCH_CHECK();
+  Sweep2Params P;
+  P.LU = LU; P.ld = ld; P.n = n; P.cbase = cbase; P.kb_begin = kb_begin; P.kb_end = kb_end; P.nblk = nblk;
+  P.X = X; P.Y = Y; P.ticket = h->sweep_ticket; P.ticket_base = h->sweep_ticket_count; P.err = h->sweep_err;
+  const int nrowblocks = upper ? kb_end : nblk - kb_begin;
+  const int grid = nrowblocks < h->num_sms ? nrowblocks : h->num_sms;
+  h->sweep_ticket_count += (unsigned int)(nrowblocks + grid);      // every CTA draws one ticket past the end
+  if (nr == 1) return upper ? launch_sweep2<true, 1>(h, P, grid, st) : launch_sweep2<false, 1>(h, P, grid, st);
+  return upper ? launch_sweep2<true, SOLVE_MAX_RHS>(h, P, grid, st) : launch_sweep2<false, SOLVE_MAX_RHS>(h, P, grid, st);
+}
+
 static int ensure_solve_attrs() {
   static bool attr = false;
   if (!attr) {
@@ -617,6 +926,11 @@ static int solve_chunk(UpdesLU *h, const double *LU, double *X, double *Y, int n
     if (rc) return rc;
     return tri_block_sweep(h->num_sms, LU, h->ld, n, true, 0, 0, n, Y, X, nrhs, st);
   }
+  if (h->solve_variant == 2) {
+    int rc = tri_sweep_rowblock(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, nrhs, st);
+    if (rc) return rc;
+    return tri_sweep_rowblock(h, LU, h->ld, n, true, 0, 0, nblk, Y, X, nrhs, st);
+  }
   int rc = tri_sweep_persistent(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, nrhs, st);
   if (rc) return rc;
   return tri_sweep_persistent(h, LU, h->ld, n, true, 0, 0, nblk, Y, X, nrhs, st);
@@ -644,11 +958,11 @@ extern "C" int updes_lu_solve(UpdesLU *h, const double *LU, const int32_t *ipiv,
       UPDES_LAUNCH_CHECK();
       int rct = solve_chunk_transposed(h, LU, Xt, Yt, nf, st);
       if (rct) return rct;
-      scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Xt, n, nf, h->perm, Bf, ldb);
+      scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Xt, n, nf, h->perm, Bf, ldb, h->row_scale);
       UPDES_LAUNCH_CHECK();
       continue;
     }
-    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf);
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf, h->row_scale);
     UPDES_LAUNCH_CHECK();
     prof_begin(PROF_SOLVE, 8.0 * (double)n * (double)n, st);
     int rc = solve_chunk(h, LU, h->xbuf, h->xbuf + (size_t)SOLVE_MAX_RHS * n, nf, st);
@@ -674,7 +988,7 @@ extern "C" int updes_lu_permute_rhs(UpdesLU *h, const double *B, int64_t ldb, in
   if (ldb < h->n) return -3;
   if (!X) return -5;
   if (nrhs <= 0) return 0;
-  gather_rows_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, nrhs, h->perm, h->n, X);
+  gather_rows_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, nrhs, h->perm, h->n, X, h->row_scale);
   UPDES_LAUNCH_CHECK();
   return 0;
 }
@@ -700,7 +1014,11 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
   double *Y = h->xbuf + (size_t)SOLVE_MAX_RHS * h->n;     // scratch for the solved block
   int rc;
   // the persistent kernel works on the 128-row partition of [0, n): the column block must be aligned to it
-  if (h->solve_variant != 0 && (r0 % SB) == 0 && ((width % SB) == 0 || r0 + width == n))
+  const bool aligned = (r0 % SB) == 0 && ((width % SB) == 0 || r0 + width == n);
+  if (h->solve_variant == 2 && aligned && (nrhs == 1 || nrhs == SOLVE_MAX_RHS))
+    rc = tri_sweep_rowblock(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
+                            (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
+  else if (h->solve_variant != 0 && aligned)
     rc = tri_sweep_persistent(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
                               (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
   else
@@ -713,7 +1031,7 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
 
 extern "C" int updes_lu_set_solve_variant(UpdesLU *handle, int variant) {
   if (!handle) return -1;
-  if (variant < 0 || variant > 1) return -2;
+  if (variant < 0 || variant > 2) return -2;
   handle->solve_variant = variant;
   return 0;
 }

@@ -172,6 +172,36 @@ class CudaBackend:
     def zero_pivot(self):
         return int(self.info.item())
 
+    def nbytes(self):
+        return (self.local.numel() + sum(b.numel() for b in self.bufs)) * 8
+
+    def check_sweeps(self):
+        """Raise if a triangular sweep of this rank timed out waiting for a solved block."""
+        flags = ctypes.c_int32(0)
+        _lib.check(self.lib.updes_lu_status(self.h, ctypes.byref(flags), _lib.stream_ptr()), "updes_lu_status")
+        if flags.value:
+            raise RuntimeError("updes_b200: a triangular sweep timed out waiting for a solved block (status %d)" % flags.value)
+
+    # ---- row equilibration (rows are spread over all ranks: the maxima are combined by the caller) ---------
+    def row_absmax(self):
+        out = self.torch.empty(self.n, dtype=self.torch.float64, device=self.device)
+        rc = self.lib.updes_row_absmax(self.local.data_ptr(), self.n, self.cols, self.ld, out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "updes_row_absmax")
+        return out
+
+    def apply_row_scale(self, absmax):
+        """Scale the local columns by 2^-floor(log2 absmax) per row and make the solves scale right-hand sides."""
+        self.scale = self.torch.empty_like(absmax)
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.updes_scale_from_absmax(absmax.data_ptr(), self.n, self.scale.data_ptr(), st), "updes_scale_from_absmax")
+        _lib.check(self.lib.updes_row_scale(self.local.data_ptr(), self.n, self.cols, self.ld, self.scale.data_ptr(), st), "updes_row_scale")
+        _lib.check(self.lib.updes_lu_set_row_scale(self.h, self.scale.data_ptr()), "updes_lu_set_row_scale")
+
+    def event(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.updes_lu_destroy(self.h)
@@ -192,14 +222,29 @@ class DistributedLU:
         self.dist = dist
         self.layout, self.rank, self.be, self.group = layout, rank, backend, group
         self.factored = False
+        self.timeline = None          # set to [] to record per-panel events (bench.py's critical-path breakdown)
+
+    def _src(self, r):
+        """`layout` ranks are ranks of `group`; torch.distributed.broadcast wants the global rank."""
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
     def _bcast(self, slot, r0, src, async_op):
-        return self.dist.broadcast(self.be.message(slot, r0), src=src, group=self.group, async_op=async_op)
+        return self.dist.broadcast(self.be.message(slot, r0), src=self._src(src), group=self.group, async_op=async_op)
+
+    def equilibrate(self):
+        """Row equilibration before pivoting: per-row max |entry| over ALL ranks' columns (all-reduce MAX of n
+        doubles), then every rank scales its columns by the same exact power of two."""
+        m = self.be.row_absmax()
+        self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX, group=self.group)
+        self.be.apply_row_scale(m)
+        return self
 
     def factor(self):
         L, be, me = self.layout, self.be, self.rank
         nb = L.nb
         ncols_local = L.local_cols(me)
+        tl = self.timeline
+        mark = (lambda: be.event()) if tl is not None else (lambda: None)
         # panel 0
         if L.owner(0) == me:
             be.panel_factor(0, 0, L.width(0))
@@ -207,7 +252,10 @@ class DistributedLU:
         pending = self._bcast(0, 0, L.owner(0), async_op=True)
         for k in range(L.nblocks):
             slot, r0, w = k % 2, k * nb, L.width(k)
+            t_begin = mark()
             pending.wait()                       # panel k (and its pivots) is in bufs[slot]
+            t_have = mark()
+            t_look = t_fact = None
             if L.owner(k) != me:
                 be.unpack_pivots(slot, r0, w)
             # interchanges on the already-factored columns to the left (L stored in final row order)
@@ -220,17 +268,34 @@ class DistributedLU:
                 if L.owner(nxt) == me:
                     lc1 = L.local_offset(nxt)
                     be.apply_panel(slot, r0, w, lc1, lc1 + w1)          # look-ahead: next panel's columns first
+                    t_look = mark()
                     be.panel_factor(r1, lc1, w1)
                     be.pack(1 - slot, r1, lc1, w1)
+                    t_fact = mark()
                     pending = self._bcast(1 - slot, r1, me, async_op=True)
                     be.apply_panel(slot, r0, w, lc1 + w1, ncols_local)  # the rest of update k
                 else:
                     pending = self._bcast(1 - slot, r1, L.owner(nxt), async_op=True)
                     be.apply_panel(slot, r0, w, right0, ncols_local)
             # last panel: nothing to the right
+            if tl is not None:
+                tl.append((k, t_begin, t_have, t_look, t_fact, mark()))
         be.set_pivots()
         self.factored = True
         return self
+
+    def timeline_ms(self):
+        """Per-panel durations on this rank (ms): wait for the panel broadcast, look-ahead update of the next panel's
+        columns, its factorisation + packing (owner only), the rest of the trailing update."""
+        out = []
+        for k, t0, t1, t2, t3, t4 in self.timeline or []:
+            rec = {"k": k, "wait": t0.elapsed_time(t1)}
+            if t2 is not None:
+                rec.update(lookahead=t1.elapsed_time(t2), panel=t2.elapsed_time(t3), update=t3.elapsed_time(t4))
+            else:
+                rec.update(update=t1.elapsed_time(t4))
+            out.append(rec)
+        return out
 
     def solve(self, b_host):
         """Solve K x = b (b: length-n host array, identical on all ranks) -> x as a device/host vector
@@ -244,10 +309,10 @@ class DistributedLU:
             r0, w = j * nb, L.width(j)
             if L.owner(j) == me:
                 be.block_sweep(False, r0, L.local_offset(j), w, x)
-            dist.broadcast(x[r0:], src=L.owner(j), group=self.group)
+            dist.broadcast(x[r0:], src=self._src(L.owner(j)), group=self.group)
         for j in range(L.nblocks - 1, -1, -1):                       # backward, upper
             r0, w = j * nb, L.width(j)
             if L.owner(j) == me:
                 be.block_sweep(True, r0, L.local_offset(j), w, x)
-            dist.broadcast(x[:r0 + w], src=L.owner(j), group=self.group)
+            dist.broadcast(x[:r0 + w], src=self._src(L.owner(j)), group=self.group)
         return x

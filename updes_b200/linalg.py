@@ -28,17 +28,41 @@ class LUFactorization:
         self._handle = handle
         self.factored = False
 
-    def factor(self):
-        """Enqueue the factorisation on the current stream (asynchronous)."""
-        rc = self._lib.updes_lu_factor(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(), self.info.data_ptr(),
-                                       _lib.stream_ptr())
-        _lib.check(rc, "updes_lu_factor")
+    def factor(self, equilibrate=False):
+        """Enqueue the factorisation on the current stream (asynchronous).  ``equilibrate``: scale every
+        row by the power of two that brings its largest magnitude into [1, 2) before pivoting; the factors
+        are kept in ``self.scale`` and applied to right-hand sides by ``solve``."""
+        if equilibrate:
+            torch = _lib.require_cuda()
+            self.scale = torch.empty(self.n, dtype=torch.float64, device=self.K.device)
+            rc = self._lib.updes_lu_factor_scaled(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(),
+                                                  self.scale.data_ptr(), self.info.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "updes_lu_factor_scaled")
+        else:
+            self.scale = None
+            rc = self._lib.updes_lu_factor(self._handle, self.K.data_ptr(), self.ipiv.data_ptr(), self.info.data_ptr(),
+                                           _lib.stream_ptr())
+            _lib.check(rc, "updes_lu_factor")
         self.factored = True
         return self
 
     def zero_pivot(self) -> int:
-        """0, or the 1-based index of the first exactly-zero pivot (synchronises)."""
+        """0, or the 1-based index of the first exactly-zero pivot (synchronises).  Negative values are
+        internal failures (see ``check``)."""
         return int(self.info.item())
+
+    def check(self) -> int:
+        """Raise ``RuntimeError`` if a device-side wait timed out (the panel kernel's grid barrier: info < 0;
+        a triangular sweep: status bit 0) -- results are garbage then and must not be returned.  Otherwise
+        the LAPACK-style status: 0, or the 1-based column of the first exactly-zero pivot."""
+        info = int(self.info.item())
+        if info < 0:
+            raise RuntimeError("updes_b200: the panel kernel's grid barrier timed out (info = %d); the factors are invalid" % info)
+        flags = ctypes.c_int32(0)
+        _lib.check(self._lib.updes_lu_status(self._handle, ctypes.byref(flags), _lib.stream_ptr()), "updes_lu_status")
+        if flags.value:
+            raise RuntimeError("updes_b200: a triangular sweep timed out waiting for a solved block (status %d)" % flags.value)
+        return info
 
     def solve(self, B, transpose=False):
         """Solve K X = B (or K^T X = B) in place.  B: (nrhs, ldb>=n) or (n,) CUDA float64; returns B."""

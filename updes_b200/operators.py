@@ -13,6 +13,7 @@ assembly kernel.  Anything that is not linear in the built-in term set raises ``
 """
 from __future__ import annotations
 
+import hashlib
 import numbers
 import warnings
 from collections import OrderedDict
@@ -209,38 +210,95 @@ class BatchPoints(np.ndarray):
         return np.asarray(super().__getitem__(idx))
 
 
-def lower_diff_operator(diff_operator, cloud, rbf, diff_args=None):
-    """Call the user's operator once per basis family with symbolic jets; return the (Ni, 5)
-    coefficient tables for RBF columns and monomial columns (reference assembly.py:93-137)."""
-    Ni, N = cloud.Ni, cloud.N
-    x = BatchPoints(cloud.sorted_nodes[:Ni].T)
-    if diff_args:
-        F = np.stack([np.asarray(a, dtype=np.float64) for a in diff_args], axis=-1)    # (N, ..., nf)
-        if F.shape[0] != N:
-            raise ValueError("diff_args fields must have one value per node (N = %d)" % N)
-        fields = np.moveaxis(F[:Ni], 0, -1)                                            # (..., nf, Ni)
-    else:
-        fields = np.ones((1, Ni))                                                      # assembly.py:114
+# Number of rows of the batched operator call in flight (None outside one).  Lets the field evaluators
+# recognise a (2, rows) coordinate array that the user's operator rebuilt from ``x`` (``np.stack([x[0],
+# x[1]])`` -- the usual port of ``jnp.array([x[0], x[1]])``) and therefore lost the BatchPoints type.
+_BATCH_ROWS = None
 
-    def run(center, monomial):
-        out = diff_operator(x, center, rbf, monomial, fields)
-        if isinstance(out, JetVector):
-            raise OperatorLoweringError("the differential operator must return a scalar, got a nodal gradient")
-        if not isinstance(out, Jet):
-            raise OperatorLoweringError(
-                "the differential operator returned %r, which does not involve the basis function; it must be a "
-                "linear combination of nodal_value / nodal_gradient / nodal_laplacian / nodal_div_grad" % (out,))
+
+class _batch_rows:
+    def __init__(self, rows): self.rows = rows
+    def __enter__(self):
+        global _BATCH_ROWS
+        self.prev, _BATCH_ROWS = _BATCH_ROWS, self.rows
+    def __exit__(self, *a):
+        global _BATCH_ROWS
+        _BATCH_ROWS = self.prev
+
+
+def _fields_table(diff_args, N, Ni):
+    """``jnp.stack(diff_args, axis=-1)`` restricted to the internal rows (assembly.py:114, :128); arrays of
+    length N+M (coefficient vectors) are accepted and cut to the nodes, as ``fields[i]`` does in the reference."""
+    if not diff_args:
+        return None
+    cols = []
+    for a in diff_args:
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 0 or a.shape[0] < Ni:
+            raise ValueError("diff_args fields must have one value per node (N = %d), got shape %s" % (N, a.shape))
+        cols.append(a[:Ni])
+    try:
+        return np.stack(cols, axis=-1)                                                 # (Ni, ..., nf)
+    except ValueError as e:
+        raise ValueError("diff_args fields must share one shape: %s" % e)
+
+
+def _coef_table(out, Ni):
+    if isinstance(out, JetVector):
+        raise OperatorLoweringError("the differential operator must return a scalar, got a nodal gradient")
+    if not isinstance(out, Jet):
+        raise OperatorLoweringError(
+            "the differential operator returned %r, which does not involve the basis function; it must be a "
+            "linear combination of nodal_value / nodal_gradient / nodal_laplacian / nodal_div_grad" % (out,))
+    tab = np.empty((Ni, 5))
+    for k in range(5):
+        c = np.asarray(out.coef[k], dtype=np.float64)
+        if c.ndim > 1 or (c.ndim == 1 and c.shape[0] != Ni):
+            raise OperatorLoweringError("operator coefficient %d has shape %s; expected a scalar or one value per row" % (k, c.shape))
+        tab[:, k] = c
+    return tab
+
+
+def lower_diff_operator(diff_operator, cloud, rbf, diff_args=None):
+    """Return the (Ni, 5) coefficient tables of the user's operator on RBF columns and on monomial columns
+    (reference assembly.py:93-137).
+
+    Fast path: ONE call per basis family with symbolic jets and the coordinates / fields of all internal
+    rows at once (``x`` of shape (2, Ni), ``fields`` of shape (nf, Ni)).  Operators that only make sense
+    for one node at a time -- a Python ``if`` on a coordinate, ``float(x[0])``, shape-dependent code:
+    the reference vmaps the operator over nodes, so ``x`` is a (2,) point there (assembly.py:126-130) --
+    make that call raise; the operator is then evaluated row by row with exactly the reference's
+    per-node arguments (``x`` (2,), ``fields[i]`` (nf,)).  Genuinely unsupported operators raise
+    ``OperatorLoweringError`` from both paths."""
+    Ni, N = cloud.Ni, cloud.N
+    F = _fields_table(diff_args, N, Ni)
+    x = BatchPoints(cloud.sorted_nodes[:Ni].T)
+    fields = np.ones((1, Ni)) if F is None else np.moveaxis(F, 0, -1)                 # (..., nf, Ni); assembly.py:114
+
+    def run_batch(center, monomial):
+        with _batch_rows(Ni):
+            return _coef_table(diff_operator(x, center, rbf, monomial, fields), Ni)
+
+    def run_rows(center, monomial):
         tab = np.empty((Ni, 5))
-        for k in range(5):
-            c = np.asarray(out.coef[k], dtype=np.float64)
-            if c.ndim > 1 or (c.ndim == 1 and c.shape[0] != Ni):
-                raise OperatorLoweringError("operator coefficient %d has shape %s; expected a scalar or one value per row" % (k, c.shape))
-            tab[:, k] = c
-        if not np.all(np.isfinite(tab)):
-            raise OperatorLoweringError("operator coefficients are not finite")
+        ones = np.ones(1)
+        for i in range(Ni):
+            out = diff_operator(np.array(cloud.sorted_nodes[i]), center, rbf, monomial, ones if F is None else F[i])
+            tab[i] = _coef_table(out, 1)[0]
         return tab
 
-    return run(_CENTER, None), run(None, _MONOMIAL)
+    tabs = []
+    for center, monomial in ((_CENTER, None), (None, _MONOMIAL)):
+        try:
+            tab = run_batch(center, monomial)
+        except OperatorLoweringError:
+            raise
+        except Exception:
+            tab = run_rows(center, monomial)      # reference semantics: one node per call
+        if not np.all(np.isfinite(tab)):
+            raise OperatorLoweringError("operator coefficients are not finite")
+        tabs.append(tab)
+    return tabs[0], tabs[1]
 
 
 # ==================================================================================================
@@ -252,8 +310,15 @@ def _points(x):
         return np.ascontiguousarray(np.asarray(x).T), "batch"
     x = np.asarray(x, dtype=np.float64)
     if x.ndim == 1:
+        if x.shape[0] != 2:
+            raise ValueError("a single evaluation point must have 2 coordinates, got shape %s" % (x.shape,))
         return x.reshape(1, 2), "single"
-    return np.ascontiguousarray(x.reshape(-1, 2)), "rows"
+    if _BATCH_ROWS is not None and x.ndim == 2 and x.shape == (2, _BATCH_ROWS):
+        # inside a batched operator call: coordinates rebuilt from x[0], x[1] (lost the BatchPoints type)
+        return np.ascontiguousarray(x.T), "batch"
+    if x.ndim != 2 or x.shape[1] != 2:
+        raise ValueError("evaluation points must be (2,), (R, 2) or the operator's own x; got shape %s" % (x.shape,))
+    return np.ascontiguousarray(x), "rows"
 
 
 def _jets(x, field, centers, rbf):
@@ -308,6 +373,16 @@ value_vec = value
 gradient_vec = gradient
 laplacian_vec = laplacian
 divergence_vec = divergence
+
+
+def interpolate_field(field, cloud1, cloud2):
+    """Carry a nodal field from ``cloud1`` to ``cloud2``: the same nodes, numbered differently because the
+    boundary types differ (reference operators.py:457-480; a permutation, no arithmetic).  Used by the
+    projection loop of demos/NavierStokes/30_channel_flow_blowing_suction.py:161-213."""
+    assert cloud1.N == cloud2.N, "the two clouds do not contain the same number of nodes"
+    field = np.asarray(field)
+    field_orig = field[np.asarray(cloud1._new_of_old)]          # original numbering
+    return field_orig[np.asarray(cloud2._old_of_new)]
 
 
 # ==================================================================================================
@@ -372,40 +447,78 @@ def boundary_conditions_func_to_arr(boundary_conditions, cloud):
 # Solver
 # ==================================================================================================
 class SteadySol:
-    """(vals, coeffs, mat) -- reference ``SteadySol`` namedtuple (utils.py:148).  ``mat`` (the
-    reference's B = diffMat inv(A)[:, :N]) needs inv(A) and is only computed when read."""
+    """``SteadySol(vals, coeffs, mat)`` -- stands in for the reference's namedtuple
+    ``PDESolution`` (utils.py:148): attribute access, indexing, unpacking, ``len``, ``_fields``,
+    ``_replace`` and ``_asdict`` behave as on the namedtuple.  The one difference is that ``mat`` (the
+    reference's B = diffMat inv(A)[:, :N], assembly.py:396-401, which needs inv(A) and a second N x N
+    matrix) is computed the first time it is read; the thunk holds host-side descriptors only, never the
+    factored system, so keeping solutions around does not pin HBM."""
+    __slots__ = ("vals", "coeffs", "_mat", "_mat_fn")
     _fields = ("vals", "coeffs", "mat")
 
-    def __init__(self, vals, coeffs, mat_fn=None):
-        self.vals, self.coeffs, self._mat_fn, self._mat = vals, coeffs, mat_fn, None
+    def __init__(self, vals, coeffs, mat=None, mat_fn=None):
+        self.vals, self.coeffs, self._mat, self._mat_fn = vals, coeffs, mat, mat_fn
 
     @property
     def mat(self):
         if self._mat is None and self._mat_fn is not None:
             self._mat = self._mat_fn()
+            self._mat_fn = None
         return self._mat
 
+    def __len__(self):
+        return 3
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self[k] for k in range(3)[i])
+        i = i + 3 if i < 0 else i
+        if i == 0: return self.vals
+        if i == 1: return self.coeffs
+        if i == 2: return self.mat
+        raise IndexError("tuple index out of range")
+
     def __iter__(self):
-        return iter((self.vals, self.coeffs, self.mat))
+        yield self.vals
+        yield self.coeffs
+        yield self.mat
+
+    def _replace(self, **kw):
+        bad = set(kw) - set(self._fields)
+        if bad:
+            raise ValueError("Got unexpected field names: %r" % sorted(bad))
+        lazy = "mat" not in kw and self._mat is None
+        return SteadySol(kw.get("vals", self.vals), kw.get("coeffs", self.coeffs),
+                         None if lazy else kw.get("mat", self._mat), self._mat_fn if lazy else None)
+
+    def _asdict(self):
+        return {"vals": self.vals, "coeffs": self.coeffs, "mat": self.mat}
 
     def __repr__(self):
-        return "PDESolution(vals=%r, coeffs=%r, mat=<lazy>)" % (self.vals, self.coeffs)
+        return "PDESolution(vals=%r, coeffs=%r, mat=%s)" % (self.vals, self.coeffs, "<lazy>" if self._mat is None else repr(self._mat))
+
+
+FactorizationError = RuntimeError     # internal device-side failures (never a numerical status) raise RuntimeError
 
 
 class _System:
     """An assembled + factored collocation system resident on the GPU."""
 
-    def __init__(self, cloud, kind, param, M, table):
+    def __init__(self, cloud, kind, param, M, table, equilibrate=True):
         self.kind, self.param, self.M = kind, param, M
         self.cloud = cloud                   # the cache key uses id(cloud): keep it alive while cached
         self.rows = _asm.DeviceRows(cloud, table)
         self.K = _asm.assemble_system(self.rows, kind, param, M)
         self.n = cloud.N + M
-        self.lu = LUFactorization(self.K, self.n).factor()
+        self.lu = LUFactorization(self.K, self.n).factor(equilibrate=equilibrate)
+
+    def check(self):
+        """Raise on internal failures; return the LAPACK-style zero-pivot status (0 = none)."""
+        return self.lu.check()
 
     def solve(self, rhs, refine=1):
-        """rhs: (n,) numpy -> coefficients (n,) numpy.  `refine` steps of iterative refinement with
-        a matrix-free residual (no second copy of K)."""
+        """rhs: (n,) numpy or CUDA tensor -> coefficients (n,) CUDA tensor.  `refine` steps of iterative
+        refinement with a matrix-free residual (no second copy of K)."""
         torch = self.rows.torch
         b = torch.as_tensor(rhs, dtype=torch.float64).to(self.K.device)
         c = self.lu.solve(b.clone())
@@ -417,15 +530,43 @@ class _System:
     def nbytes(self):
         return self.K.numel() * 8
 
+    @staticmethod
+    def predict_nbytes(n, world=1):
+        return n * _asm.padded_ld(n) * 8
 
-def _dist_world():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_world_size(), dist.get_rank()
-    except Exception:
-        pass
-    return 1, 0
+
+# ---- multi-GPU opt-in ---------------------------------------------------------------------------------
+_DIST = {"enabled": False, "group": None}
+
+
+def enable_distributed(group=None):
+    """Shard every subsequent ``pde_solver*`` call over the ranks of ``group`` (default: the default
+    ``torch.distributed`` process group, which must already be initialised with the NCCL backend, one
+    process per GPU).  EVERY rank of the group must then call the solver with identical arguments.
+    Opt-in on purpose: an initialised process group alone (e.g. inside an unrelated data-parallel job)
+    does not change how ``pde_solver`` runs."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("enable_distributed() needs an initialised torch.distributed process group (backend nccl)")
+    _DIST["enabled"], _DIST["group"] = True, group
+    clear_cache()
+
+
+def disable_distributed():
+    _DIST["enabled"], _DIST["group"] = False, None
+    clear_cache()
+
+
+def _dist_world(distributed=None):
+    """(world, rank, group) of the sharded path, or (1, 0, None) when it is off."""
+    on = _DIST["enabled"] if distributed is None else bool(distributed)
+    if not on:
+        return 1, 0, None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("distributed=True needs an initialised torch.distributed process group")
+    g = _DIST["group"]
+    return dist.get_world_size(g), dist.get_rank(g), g
 
 
 def default_block_width(n, world):
@@ -439,66 +580,117 @@ def default_block_width(n, world):
 
 
 class _DistSystem:
-    """The same system sharded column-block-cyclically over all ranks of the default process group
+    """The same system sharded column-block-cyclically over the ranks of a process group
     (updes_b200/distributed.py).  Every rank calls pde_solver with identical arguments."""
 
-    def __init__(self, cloud, kind, param, M, table, world, rank):
+    def __init__(self, cloud, kind, param, M, table, world, rank, group=None):
         from .distributed import ColumnBlockCyclic, CudaBackend, DistributedLU
         self.kind, self.param, self.M = kind, param, M
         self.cloud = cloud                   # the cache key uses id(cloud): keep it alive while cached
+        self.group = group
         self.rows = _asm.DeviceRows(cloud, table)
         self.n = cloud.N + M
         self.layout = ColumnBlockCyclic(self.n, default_block_width(self.n, world), world)
         self.be = CudaBackend(self.layout, rank)
         self.be.assemble(self.rows, kind, param, M)
-        self.dlu = DistributedLU(self.layout, rank, self.be).factor()
-        self.lu = self                       # zero_pivot() interface of LUFactorization
+        self.dlu = DistributedLU(self.layout, rank, self.be, group=group).factor()
         self.K = self.be.local
 
-    def zero_pivot(self):
+    def check(self):
         import torch.distributed as dist
         t = self.be.info.clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lo = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        if int(lo.item()) < 0:
+            raise FactorizationError("the panel kernel's grid barrier timed out on some rank (info = %d)" % int(lo.item()))
+        self.be.check_sweeps()
         return int(t.item())
 
     def solve(self, rhs, refine=1):
         torch = self.rows.torch
         b = torch.as_tensor(rhs, dtype=torch.float64).to(self.be.device)
-        c = self.dlu.solve(rhs)
+        c = self.dlu.solve(b)
         for _ in range(refine):
             r = b - _asm.apply_rows(self.rows, self.kind, self.param, self.M, c.view(1, -1))[0]
             c = c + self.dlu.solve(r)
         return c
 
     def nbytes(self):
-        return self.be.local.numel() * 8
+        return self.be.nbytes()
+
+    @staticmethod
+    def predict_nbytes(n, world):
+        nb = default_block_width(n, world)
+        cols = -(-n // world) + nb
+        return n * _asm.padded_ld(cols) * 8 + 2 * (n * nb + nb) * 8
 
 
-_CACHE: "OrderedDict[tuple, _System]" = OrderedDict()
-_CACHE_BYTES = 80 << 30
+# ---- cache of factored systems -----------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, object]" = OrderedDict()
+_CACHE_FRACTION = 0.88        # of the device's total memory, shared by all cached systems
 
 
 def clear_cache():
-    """Drop every cached factorisation (frees the HBM they hold)."""
+    """Drop every cached factorisation (frees the HBM they hold, whatever solutions are still referenced)."""
     _CACHE.clear()
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+    except Exception:
+        pass
 
 
-def _cached_system(key, build):
+def cache_budget_bytes():
+    torch = _lib.require_cuda()
+    free, total = torch.cuda.mem_get_info()
+    return int(_CACHE_FRACTION * total)
+
+
+def _cached_system(key, build, need_bytes):
+    """LRU cache keyed on (cloud, rbf, lowered operator, ...).  Space for the new system is made BEFORE it
+    is built (evicting least-recently-used systems until the prediction fits the device budget), so the
+    peak is never more than the budget plus transients."""
     sys_ = _CACHE.get(key)
     if sys_ is not None:
         _CACHE.move_to_end(key)
         return sys_
+    torch = _lib.require_cuda()
+    budget = cache_budget_bytes()
+    evicted = False
+    while _CACHE and sum(s.nbytes() for s in _CACHE.values()) + need_bytes > budget:
+        _CACHE.popitem(last=False)
+        evicted = True
+    if evicted or torch.cuda.mem_get_info()[0] < need_bytes * 1.02:
+        torch.cuda.empty_cache()
     sys_ = build()
     _CACHE[key] = sys_
-    while len(_CACHE) > 1 and sum(s.nbytes() for s in _CACHE.values()) > _CACHE_BYTES:
-        _CACHE.popitem(last=False)
     return sys_
 
 
-def _interp_system(cloud, kind, param, M):
-    """Factorisation of A = [[Phi P], [P^T 0]] (assembly.py:62-90), cached per (cloud, rbf, M)."""
-    key = ("A", id(cloud), kind, param, M)
-    return _cached_system(key, lambda: _System(cloud, kind, param, M, _asm.build_interpolation_rows(cloud)))
+def _digest(*arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b"-")
+        else:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.shape).encode()); h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def _interp_system(cloud, kind, param, M, distributed=None):
+    """Factorisation of A = [[Phi P], [P^T 0]] (assembly.py:62-90), cached per (cloud, rbf, M).  On the
+    multi-GPU path A is sharded like K (an (N+M)^2 matrix per rank would not fit at the sizes that path is for)."""
+    world, rank, group = _dist_world(distributed)
+    key = ("A", id(cloud), kind, param, M, world)
+    n = cloud.N + M
+    if world > 1:
+        return _cached_system(key, lambda: _DistSystem(cloud, kind, param, M, _asm.build_interpolation_rows(cloud), world, rank, group),
+                              _DistSystem.predict_nbytes(n, world))
+    return _cached_system(key, lambda: _System(cloud, kind, param, M, _asm.build_interpolation_rows(cloud)),
+                          _System.predict_nbytes(n))
 
 
 def core_compute_coefficients(field, cloud, rbf, nb_monomials):
@@ -529,7 +721,16 @@ def assemble_q(rhs_operator, boundary_conditions, cloud, rbf, nb_monomials, rhs_
         fields = None
     x = BatchPoints(cloud.sorted_nodes[:Ni].T)
     q = np.zeros(N)
-    q[:Ni] = np.broadcast_to(np.asarray(rhs_operator(x, cloud.sorted_nodes, rbf, fields), dtype=np.float64), (Ni,))
+    try:
+        with _batch_rows(Ni):
+            q_int = np.asarray(rhs_operator(x, cloud.sorted_nodes, rbf, fields), dtype=np.float64)
+        q[:Ni] = np.broadcast_to(q_int, (Ni,))
+    except OperatorLoweringError:
+        raise
+    except Exception:
+        # per-node evaluation, the reference's vmap semantics (assembly.py:466-469): x is one (2,) point
+        for i in range(Ni):
+            q[i] = float(rhs_operator(np.array(cloud.sorted_nodes[i]), cloud.sorted_nodes, rbf, fields))
     for f_id in cloud.facet_types.keys():
         assert f_id in boundary_conditions.keys(), "facets and boundary functions don't match ids"
         bd = boundary_conditions[f_id]
@@ -539,13 +740,14 @@ def assemble_q(rhs_operator, boundary_conditions, cloud, rbf, nb_monomials, rhs_
 
 
 def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max_degree, diff_args=None,
-               rhs_args=None, refine=1):
+               rhs_args=None, *, refine=1, distributed=None):
     """Solve a linear PDE by global RBF collocation (reference operators.py:559-618).
 
-    Same arguments and result as the reference.  The factorisation is cached on (cloud, rbf,
+    Same positional arguments and result as the reference.  The factorisation is cached on (cloud, rbf,
     max_degree, lowered operator, Robin betas): repeated calls with an unchanged left-hand side --
     the time loops of demos/Advection -- only pay for the right-hand side and two triangular sweeps.
-    """
+    Keyword-only extras: ``refine`` (iterative-refinement steps, default 1), ``distributed`` (None = follow
+    ``enable_distributed()``; True/False forces the sharded / single-GPU path for this call)."""
     kind, param = identify_rbf(rbf)
     robin_coeffs, boundary_conditions = duplicate_robin_coeffs(dict(boundary_conditions), cloud)
     boundary_conditions = zerofy_periodic_cond(boundary_conditions, cloud)
@@ -553,56 +755,62 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     coef_phi, coef_pol = lower_diff_operator(diff_operator, cloud, rbf, diff_args)
     betas = np.array([robin_coeffs[k] for k in sorted(robin_coeffs)], dtype=np.float64) if robin_coeffs else None
 
-    key = ("K", id(cloud), kind, param, M, coef_phi.tobytes(), coef_pol.tobytes(), None if betas is None else betas.tobytes())
-    world, rank = _dist_world()
+    world, rank, group = _dist_world(distributed)
+    key = ("K", id(cloud), kind, param, M, _digest(coef_phi, coef_pol, betas), world)
+    n = cloud.N + M
     table_fn = lambda: _asm.build_operator_rows(cloud, coef_phi, coef_pol, betas)
     if world > 1:
-        system = _cached_system(key + (world,), lambda: _DistSystem(cloud, kind, param, M, table_fn(), world, rank))
+        system = _cached_system(key, lambda: _DistSystem(cloud, kind, param, M, table_fn(), world, rank, group),
+                                _DistSystem.predict_nbytes(n, world))
     else:
-        system = _cached_system(key, lambda: _System(cloud, kind, param, M, table_fn()))
+        system = _cached_system(key, lambda: _System(cloud, kind, param, M, table_fn()), _System.predict_nbytes(n))
     q = assemble_q(rhs_operator, boundary_conditions, cloud, rbf, M, rhs_args)
     coeffs_dev = system.solve(np.concatenate([q, np.zeros(M)]), refine=refine)
-    if system.lu.zero_pivot():
-        warnings.warn("collocation matrix is exactly singular (zero pivot at column %d)" % system.lu.zero_pivot())
+    zero_pivot = system.check()              # raises FactorizationError on internal failures
+    if zero_pivot:
+        warnings.warn("collocation matrix is exactly singular (zero pivot at column %d)" % zero_pivot)
     # vals = [Phi P] c with the reference's zero-diagonal Phi (assembly.py:31-32, :404-410)
     torch = system.rows.torch
     own = torch.arange(cloud.N, dtype=torch.int32, device=coeffs_dev.device)
     jphi, jpol = _asm.eval_jets(kind, param, system.rows.centres, coeffs_dev.view(1, -1), system.rows.centres, own)
     vals = (jphi[0, :, 0] + jpol[0, :, 0]).cpu().numpy()
     coeffs = coeffs_dev.cpu().numpy()
+    # the lazy ``mat`` holds host descriptors only (never `system`): solutions must not pin the factors in HBM
+    table = system.rows.table
+    if world > 1:
+        def mat_fn():
+            raise NotImplementedError("SteadySol.mat is not available on the multi-GPU path")
+    else:
+        def mat_fn():
+            return _reference_mat(cloud, kind, param, M, table)
+    return SteadySol(vals, coeffs, None, mat_fn)
 
-    def mat_fn():
-        return _reference_mat(cloud, kind, param, M, system)
 
-    return SteadySol(vals, coeffs, mat_fn)
-
-
-def _reference_mat(cloud, kind, param, M, system):
+def _reference_mat(cloud, kind, param, M, table):
     """B = (diffMat @ inv(A))[:, :N] (assembly.py:396-401), for callers that read ``SteadySol.mat``.
-    A is symmetric, so B[r, :] = (inv(A) diffMat[r, :]^T)[:N]: N right-hand sides against the LU of A."""
-    torch = system.rows.torch
+    A is symmetric, so B[r, :] = (inv(A) diffMat[r, :]^T)[:N]: N right-hand sides against the LU of A.
+    diffMat is re-assembled from the row descriptors (the factored K no longer holds it)."""
     N = cloud.N
     if N > 20000:
         raise MemoryError("SteadySol.mat (the reference's B = diffMat inv(A)[:, :N]) needs N = %d right-hand sides "
                           "against inv(A) and a second N x N matrix; it is only provided for N <= 20000" % N)
-    if isinstance(system, _DistSystem):
-        raise NotImplementedError("SteadySol.mat is not available on the multi-GPU path")
-    D = _asm.assemble_system(system.rows, kind, param, M)[:N].contiguous()     # fresh copy: K holds LU now
-    X = _interp_system(cloud, kind, param, M).lu.solve(D)
+    rows = _asm.DeviceRows(cloud, table)
+    D = _asm.assemble_system(rows, kind, param, M)[:N].contiguous()
+    X = _interp_system(cloud, kind, param, M, distributed=False).lu.solve(D)
     return X[:, :N].cpu().numpy()
 
 
 def pde_solver_jit_with_bc(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max_degree, diff_args=None,
-                           rhs_args=None):
+                           rhs_args=None, **kw):
     """operators.py:621-625.  There is no tracing compiler here: identical to ``pde_solver``."""
-    return pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max_degree, diff_args, rhs_args)
+    return pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max_degree, diff_args, rhs_args, **kw)
 
 
 def pde_solver_jit(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max_degree, diff_args=None,
-                   rhs_args=None):
+                   rhs_args=None, **kw):
     """operators.py:650-683: boundary callables are turned into arrays first."""
     bc = boundary_conditions_func_to_arr(boundary_conditions, cloud)
-    return pde_solver_jit_with_bc(diff_operator, rhs_operator, cloud, bc, rbf, max_degree, diff_args, rhs_args)
+    return pde_solver_jit_with_bc(diff_operator, rhs_operator, cloud, bc, rbf, max_degree, diff_args, rhs_args, **kw)
 
 
 def pde_multi_solver(diff_operators, rhs_operators, cloud, boundary_conditions, rbf, max_degree, nb_iters=10, tol=1e-6,
