@@ -43,3 +43,37 @@ def cloud_from_golden(name):
     facet_types = {nm: str(t) for nm, t in zip(names, g["facet_types"])}
     return u.Cloud.from_arrays(g["sorted_nodes"], g["counts"], g["Np"], facet_types, facet_nodes, g["sorted_outward_normals"],
                                old_of_new=g["old_of_new"] if "old_of_new" in g else None), g
+
+
+def true_rel_err(got, want, floor=1e-6):
+    """TRUE per-entry relative error |got - want| / |want| over the entries that are not near-cancellations
+    (|want| > floor * largest magnitude of the row) -- reported next to the row-scaled figure."""
+    got = np.asarray(got); want = np.asarray(want)
+    big = np.abs(want) > floor * np.max(np.abs(want), axis=-1, keepdims=True)
+    return float(np.max(np.abs(got - want)[big] / np.abs(want)[big])) if np.any(big) else 0.0
+
+
+def exact_solution(K, rhs, A_rows):
+    """The discrete collocation solution to (almost) working-precision-independent accuracy: K c = rhs solved by
+    LAPACK LU + iterative refinement with 80-bit (numpy longdouble) residuals, then vals = [Phi P] c in longdouble.
+    Converges as long as cond(K) * 2^-53 < 1.  Lets a test say how far EACH formulation (the reference's
+    inv + GEMM + QR, and the product's LU) is from the solution both approximate."""
+    import scipy.linalg as sla
+    lu = sla.lu_factor(K)
+    Kl, rl = K.astype(np.longdouble), rhs.astype(np.longdouble)
+    c = sla.lu_solve(lu, rhs).astype(np.longdouble)
+    for _ in range(8):
+        r = rl - Kl @ c
+        d = sla.lu_solve(lu, np.asarray(r, dtype=np.float64))
+        c = c + d.astype(np.longdouble)
+        if np.max(np.abs(d)) <= 1e-17 * np.max(np.abs(c)):
+            break
+    vals = A_rows.astype(np.longdouble) @ c
+    return np.asarray(vals, dtype=np.float64), np.asarray(c, dtype=np.float64)
+
+
+def backward_error(K, c, rhs):
+    """normwise backward error ||K c - rhs||_inf / (||K||_inf ||c||_inf + ||rhs||_inf)"""
+    Kl = K.astype(np.longdouble)
+    r = np.asarray(Kl @ c.astype(np.longdouble) - rhs.astype(np.longdouble), dtype=np.float64)
+    return float(np.max(np.abs(r)) / (np.abs(K).sum(1).max() * np.max(np.abs(c)) + np.max(np.abs(rhs))))

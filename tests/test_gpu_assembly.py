@@ -4,7 +4,7 @@ import pytest
 
 import updes_b200 as u
 from updes_b200 import assembly as asm
-from helpers import CONFIG1_FACETS, CONFIG2_FACETS, cloud_from_golden, rel_err_rowscaled
+from helpers import CONFIG1_FACETS, CONFIG2_FACETS, cloud_from_golden, rel_err_rowscaled, true_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -34,6 +34,11 @@ def test_config1_blocks_all_kernels(oracle, kind, param, degree):
     got = _assemble_K(cloud, kind, param, M, coef)
     want = oracle.assemble_K(cloud, kind, param, M, coef)
     assert rel_err_rowscaled(got, want) <= 1e-12
+    # second number: TRUE per-entry relative error on every entry above 1e-6 of its row's largest magnitude
+    # (the row-scaled figure alone would let a tiny entry be 100 % wrong)
+    t = true_rel_err(got, want)
+    print("%s(%s) degree %d: row-scaled %.1e, true per-entry %.1e" % (kind, param, degree, rel_err_rowscaled(got, want), t))
+    assert t <= 1e-10, t
 
 
 @pytest.mark.parametrize("mask_cols", [[0], [1, 2], [3, 4], [0, 1, 2], [3], [0, 3, 4]])

@@ -82,3 +82,17 @@ def test_headline_size_entry_parity_backward_error_and_analytic_solution(oracle)
     # factor-once / solve-many: a second right-hand side reuses the factors; linearity of the solve
     x2 = lu.solve((2.0 * b).clone())
     assert float((x2 - 2.0 * x).abs().max() / x.abs().max()) <= 1e-9
+    # ---- row equilibration at the headline size: same system, rows scaled by exact powers
+    # of two before pivoting.  Reported: how many pivots change; asserted: the backward error stays <= 1e-13.
+    x_plain = x.clone()
+    del x2
+    asm.assemble_system(rows, "polyharmonic", 1.0, M, out=K)
+    lu2 = LUFactorization(K, n).factor(equilibrate=True)
+    x = lu2.solve(b.clone())
+    assert lu2.check() == 0
+    same = float(np.mean(lu2.ipiv.cpu().numpy() == piv))
+    r = b - asm.apply_rows(rows, "polyharmonic", 1.0, M, x.view(1, -1))[0]
+    berr2 = float(r.abs().max().item() / (knorm * x.abs().max().item() + b.abs().max().item()))
+    print("headline size: backward error plain %.2e, equilibrated %.2e; %.1f %% of the pivots unchanged; "
+          "solutions differ by %.2e" % (berr, berr2, 100 * same, float((x - x_plain).abs().max() / x_plain.abs().max())))
+    assert berr2 <= 1e-13, berr2

@@ -92,11 +92,11 @@ def test_lu_tall_panel_paths(cap):
     assert (K[:, :n].cpu() - lu_ref).abs().max().item() <= 1e-10 * lu_ref.abs().max().item()
 
 
-@pytest.mark.parametrize("variant", [1, 0])
-@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 1), (2051, 5), (128, 2), (129, 1), (20000, 2)])
+@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3), (1000, 1), (2051, 5), (128, 2), (129, 1), (20000, 2), (20000, 1), (5003, 4)])
 def test_lu_solve(n, nrhs, variant):
-    """Triangular solves: variant 1 = persistent pipelined sweeps (one cooperative launch per direction),
-    variant 0 = one launch per 128-row block."""
+    """Triangular solves: variant 2 = row-block streaming sweeps (default; solved blocks published through the
+    data), variant 1 = step-synchronous persistent sweeps, variant 0 = one launch per 128-row block."""
     import torch
     from updes_b200.linalg import LUFactorization
     A, K = _matrix(n, seed=10 + n, dominant=(n >= 20000))
@@ -126,6 +126,102 @@ def test_lu_solve_transposed(n, nrhs):
     assert (X - ref).abs().max().item() / ref.abs().max().item() <= 1e-9
     res = (A.T @ X.T - B.T).abs().max().item() / (A.abs().max().item() * X.abs().max().item() * n)
     assert res <= 1e-14, res
+
+
+@pytest.mark.parametrize("n", [100, 640, 2051, 9000, 12000])
+def test_panel_variants_agree_with_lapack(n):
+    """Second-generation panel kernels (implicit pivoting, REDUX arg-max, pushed cluster exchange) must give the
+    same pivots as the first-generation ones and as LAPACK; n = 9000 / 12000 cross the 8 192-row boundary between
+    the cluster kernel and the grid-wide kernel."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    A, K0 = _matrix(n, seed=3 * n)
+    _, piv_ref = torch.linalg.lu_factor(A.cuda())
+    piv_ref = piv_ref.cpu().numpy() - 1
+    facs = []
+    for variant in (2, 1, 0):
+        K = K0.clone()
+        lu = LUFactorization(K, n)
+        lu.set_panel_variant(variant)
+        lu.factor()
+        torch.cuda.synchronize()
+        assert lu.check() == 0
+        assert np.array_equal(lu.ipiv.cpu().numpy(), piv_ref), "panel variant %d: pivots differ from LAPACK" % variant
+        facs.append(K[:, :n].clone())
+    scale = facs[0].abs().max().item()
+    assert (facs[0] - facs[1]).abs().max().item() <= 1e-11 * scale
+    assert (facs[0] - facs[2]).abs().max().item() <= 1e-11 * scale
+
+
+def test_panel_ties_take_the_first_row_like_lapack():
+    """Equal magnitudes in a column: idamax takes the smallest row index, also after interchanges."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    n = 700
+    g = torch.Generator().manual_seed(9)
+    A = torch.randint(-3, 4, (n, n), generator=g, dtype=torch.int64).to(torch.float64)   # many exact ties
+    A += torch.diag(torch.full((n,), 0.5, dtype=torch.float64))
+    from updes_b200.assembly import padded_ld
+    for variant in (2, 1):
+        K = torch.zeros((n, padded_ld(n)), dtype=torch.float64); K[:, :n] = A
+        K = K.cuda()
+        lu = LUFactorization(K, n)
+        lu.set_panel_variant(variant)
+        lu.factor()
+        torch.cuda.synchronize()
+        _, piv_ref = torch.linalg.lu_factor(A)
+        # LAPACK blocks differently, so rounding may break later ties differently; the first 32-column panel is exact
+        assert np.array_equal(lu.ipiv.cpu().numpy()[:8], piv_ref.numpy()[:8] - 1)
+        F = K[:, :n].cpu()
+        L = torch.tril(F, -1) + torch.eye(n, dtype=torch.float64)
+        PA = A.clone()
+        for kk, p in enumerate(lu.ipiv.cpu().tolist()):
+            if p != kk:
+                PA[[kk, p]] = PA[[p, kk]]
+        assert (L @ torch.triu(F) - PA).abs().max().item() <= 1e-10 * n
+        assert L.abs().max().item() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("n", [300, 2051])
+def test_row_equilibrated_factorisation(n):
+    """updes_lu_factor_scaled: rows scaled by exact powers of two before pivoting; solves (plain and transposed)
+    still solve the ORIGINAL system, and the backward error no longer depends on the row scaling."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    A, K = _matrix(n, seed=n + 5)
+    g = torch.Generator().manual_seed(3)
+    rs = 10.0 ** torch.randint(-8, 9, (n,), generator=g).to(torch.float64)       # rows of wildly different scale
+    A = A * rs[:, None]
+    K[:, :n] = A.cuda()
+    lu = LUFactorization(K, n).factor(equilibrate=True)
+    torch.cuda.synchronize()
+    assert lu.check() == 0
+    sc = lu.scale.cpu()
+    m = A.abs().max(dim=1).values * sc
+    assert bool(((m >= 1.0) & (m < 2.0)).all()) and bool((torch.frexp(sc)[0] == 0.5).all())
+    B = torch.randn((2, n), generator=g, dtype=torch.float64)
+    X = lu.solve((B * rs[None]).cuda().clone()).cpu()            # right-hand side scaled like the rows
+    ref = torch.linalg.solve(A / rs[:, None], B.T).T
+    assert (X - ref).abs().max().item() / ref.abs().max().item() <= 1e-9
+    Xt = lu.solve(B.cuda().clone(), transpose=True).cpu()
+    res = (A.T @ Xt.T - B.T).abs().max().item() / ((A.abs().sum(0).max() * Xt.abs().max()).item() + B.abs().max().item())
+    assert res <= 1e-13, res
+    # the pivots are those LAPACK finds on the equilibrated matrix
+    _, piv_ref = torch.linalg.lu_factor(A * sc[:, None])
+    assert np.array_equal(lu.ipiv.cpu().numpy(), piv_ref.numpy() - 1)
+
+
+def test_internal_failure_raises():
+    """A timed-out grid barrier is reported as info = -1; check() must raise instead of returning garbage."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    A, K = _matrix(64, seed=1)
+    lu = LUFactorization(K, 64).factor()
+    torch.cuda.synchronize()
+    assert lu.check() == 0
+    lu.info.fill_(-1)
+    with pytest.raises(RuntimeError, match="grid barrier"):
+        lu.check()
 
 
 def test_lu_singular_reports_info():

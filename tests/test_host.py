@@ -221,7 +221,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-nx", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0", "--cpu-nx", "16", "--cpu-sizes", "10x8,14x14,20x20"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -230,6 +230,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["dtype"] == "f64" and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    sweep = line["cpu_baseline"]["size_sweep"]               # measured sizes + cubic extrapolation, labelled
+    assert [r["n"] for r in sweep["measured"]] == [83, 199, 403] and "EXTRAPOLATED" in sweep["note"]
+    assert sweep["extrapolated_seconds_at_n_90003"] > sweep["measured"][-1]["seconds"]
+
+
+def test_bench_reference_arm_under_torchrun_env_restores_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must lift it (rank 0 re-executes itself) and the other
+    ranks must exit 0 without output (round 1: the N >= 2 reference arms ran on one thread)."""
+    import json
+    import subprocess
+    import sys
+    base = dict(os.environ, OMP_NUM_THREADS="1", WORLD_SIZE="2", LOCAL_RANK="0")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+           "--cpu-nx", "12", "--no-cpu-sweep"]
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(base, RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+    r0 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(base, RANK="0"))
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    line = json.loads(r0.stdout.strip().splitlines()[-1])
+    assert line["config"]["host_threads_env"] == str(os.cpu_count()) and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["cores"] == os.cpu_count() or os.cpu_count() == 1
 
 
 def test_c_abi_rejects_bad_arguments_without_a_gpu():

@@ -593,7 +593,7 @@ class _DistSystem:
         self.layout = ColumnBlockCyclic(self.n, default_block_width(self.n, world), world)
         self.be = CudaBackend(self.layout, rank)
         self.be.assemble(self.rows, kind, param, M)
-        self.dlu = DistributedLU(self.layout, rank, self.be, group=group).factor()
+        self.dlu = DistributedLU(self.layout, rank, self.be, group=group).equilibrate().factor()
         self.K = self.be.local
 
     def check(self):
