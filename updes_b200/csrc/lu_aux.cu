@@ -6,31 +6,62 @@ namespace updes {
 
 // ---- row interchanges -------------------------------------------------------------------------
 // Applies interchanges (k0+t <-> ipiv[k0+t]), t = 0..npiv-1, in order, to columns [c0, c0+ncols).
-// Row-major storage makes every interchange a pair of fully coalesced row segments; one thread
-// owns two adjacent columns for the whole sequence, so the in-order semantics need no barrier.
+// A sequence of <= 32 interchanges touches <= 64 rows; executing it literally is a chain of 32 dependent
+// load/store round trips per thread (24 us per launch at 8k columns, ~20x the traffic time).  Instead warp 0
+// first composes the sequence into a permutation of the involved rows (32 steps of register/shuffle work),
+// then every thread GATHERS its column of all moved rows (all loads independent and in flight together) and
+// scatters them back: one memory round trip, fully coalesced in the row-major layout.
 constexpr int SWAP_THREADS = 128;
-constexpr int SWAP_MAX_PIV = 64;
+constexpr int SWAP_MAX_PIV = 32;
 
 __global__ void __launch_bounds__(SWAP_THREADS) swap_rows_kernel(double *K, long long ld, long long c0, long long ncols,
                                                                 long long k0, int npiv, const int32_t *ipiv) {
-  __shared__ int s_piv[SWAP_MAX_PIV];
-  if (threadIdx.x < npiv) s_piv[threadIdx.x] = ipiv[k0 + threadIdx.x];
-  __syncthreads();
-  const long long c = c0 + 2 * ((long long)blockIdx.x * SWAP_THREADS + threadIdx.x);
-  if (c >= c0 + ncols) return;
-  const bool pair = c + 1 < c0 + ncols;
-  for (int t = 0; t < npiv; t++) {
-    const long long p = s_piv[t];
-    if (p == k0 + t) continue;
-    double *ra = K + (k0 + t) * ld + c, *rb = K + p * ld + c;
-    if (pair) {
-      const double2 va = *reinterpret_cast<double2 *>(ra), vb = *reinterpret_cast<double2 *>(rb);
-      *reinterpret_cast<double2 *>(ra) = vb;
-      *reinterpret_cast<double2 *>(rb) = va;
-    } else {
-      const double va = *ra, vb = *rb;
-      *ra = vb; *rb = va;
+  // slots 0..31: the diagonal rows k0+s; slots 32..63: pivot rows outside [k0, k0+npiv), in order of first use
+  __shared__ int s_row[64];      // row held by a slot (-1: unused)
+  __shared__ int s_src[64];      // slot whose ORIGINAL content ends up in this slot
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int row_lo = lane < npiv ? (int)(k0 + lane) : -1, row_hi = -1;
+    int src_lo = lane, src_hi = lane + 32;
+    int nextra = 0;
+    for (int t = 0; t < npiv; t++) {
+      const int p = ipiv[k0 + t];
+      if (p == (int)(k0 + t)) continue;                      // uniform
+      int idx;
+      if (p < (int)(k0 + npiv)) {
+        idx = p - (int)k0;
+      } else {
+        const unsigned int hit = __ballot_sync(0xffffffffu, row_hi == p);
+        if (hit) {
+          idx = 32 + __ffs(hit) - 1;
+        } else {
+          idx = 32 + nextra;
+          if (lane == nextra) row_hi = p;
+          nextra++;
+        }
+      }
+      const int st = __shfl_sync(0xffffffffu, src_lo, t);
+      const int si = idx < 32 ? __shfl_sync(0xffffffffu, src_lo, idx) : __shfl_sync(0xffffffffu, src_hi, idx - 32);
+      if (lane == t) src_lo = si;
+      if (idx < 32) { if (lane == idx) src_lo = st; }
+      else if (lane == idx - 32) src_hi = st;
     }
+    s_row[lane] = row_lo; s_row[32 + lane] = row_hi;
+    s_src[lane] = row_lo >= 0 ? src_lo : lane;               // unused slots map to themselves: not moved
+    s_src[32 + lane] = row_hi >= 0 ? src_hi : 32 + lane;
+  }
+  __syncthreads();
+  const long long c = c0 + (long long)blockIdx.x * SWAP_THREADS + threadIdx.x;
+  if (c >= c0 + ncols) return;
+  double v[64];
+#pragma unroll
+  for (int s = 0; s < 64; s++) {
+    const int src = s_src[s];
+    if (src != s) v[s] = K[(long long)s_row[src] * ld + c];
+  }
+#pragma unroll
+  for (int s = 0; s < 64; s++) {
+    if (s_src[s] != s) K[(long long)s_row[s] * ld + c] = v[s];
   }
 }
 
@@ -40,12 +71,10 @@ int swap_rows(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t k0, int64_t 
   double *K = h->view[v].ptr;
   const long long ld = h->view[v].ld;
   if (!K) return -2;
-  if (c0 & 1) return -3;
   for (int64_t t0 = 0; t0 < npiv; t0 += SWAP_MAX_PIV) {
     const int np = (int)((npiv - t0) < SWAP_MAX_PIV ? (npiv - t0) : SWAP_MAX_PIV);
-    const long long pairs = (ncols + 1) / 2;
     prof_begin(PROF_SWAP, 32.0 * (double)ncols * np, st);
-    swap_rows_kernel<<<(unsigned)((pairs + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
+    swap_rows_kernel<<<(unsigned)((ncols + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
         K, ld, c0, ncols, k0 + t0, np, ipiv);
     prof_end(st);
     UPDES_LAUNCH_CHECK();
@@ -57,8 +86,9 @@ int swap_rows(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t k0, int64_t 
 // X = L^-1 B with L = K[r0:r0+NB, r0:r0+NB] (unit lower) and B = K[r0:r0+NB, c0:c0+ncols], in place.
 // One thread per column of B: the NB values of the column live in registers, L is broadcast from
 // shared memory; loads/stores are coalesced across the threads of a warp (adjacent columns).
+constexpr int TRSM_THREADS = 64;
 template <int NB>
-__global__ void __launch_bounds__(128) trsm_base_kernel(const double *Lm, long long ldl, long long rl, long long cl,
+__global__ void __launch_bounds__(TRSM_THREADS) trsm_base_kernel(const double *Lm, long long ldl, long long rl, long long cl,
                                                         double *B, long long ldb, long long rb, long long cb,
                                                         long long ncols) {
   __shared__ double L[NB][NB + 1];
@@ -72,12 +102,12 @@ __global__ void __launch_bounds__(128) trsm_base_kernel(const double *Lm, long l
   double x[NB];
 #pragma unroll
   for (int i = 0; i < NB; i++) x[i] = B[(rb + i) * ldb + c];
+  // column-oriented elimination: after x[j] is final, the updates of x[j+1..] are independent of each other
+  // (the row-oriented form is one dependent FMA chain of length NB(NB-1)/2 per thread)
 #pragma unroll
-  for (int i = 1; i < NB; i++) {
-    double v = x[i];
+  for (int j = 0; j < NB - 1; j++) {
 #pragma unroll
-    for (int j = 0; j < i; j++) v = fma(-L[i][j], x[j], v);
-    x[i] = v;
+    for (int i = j + 1; i < NB; i++) x[i] = fma(-L[i][j], x[j], x[i]);
   }
 #pragma unroll
   for (int i = 1; i < NB; i++) B[(rb + i) * ldb + c] = x[i];
@@ -86,12 +116,12 @@ __global__ void __launch_bounds__(128) trsm_base_kernel(const double *Lm, long l
 static int trsm_base(UpdesLU *h, int vl, int64_t rl, int64_t cl, int nb, int vb, int64_t rb, int64_t cb,
                      int64_t ncols, cudaStream_t st) {
   const MatView &VL = h->view[vl], &VB = h->view[vb];
-  const unsigned grid = (unsigned)((ncols + 127) / 128);
+  const unsigned grid = (unsigned)((ncols + TRSM_THREADS - 1) / TRSM_THREADS);
   if (nb != 32 && nb != 16 && nb != 8) return -4;
   prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
-  if (nb == 32) trsm_base_kernel<32><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
-  else if (nb == 16) trsm_base_kernel<16><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
-  else trsm_base_kernel<8><<<grid, 128, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  if (nb == 32) trsm_base_kernel<32><<<grid, TRSM_THREADS, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  else if (nb == 16) trsm_base_kernel<16><<<grid, TRSM_THREADS, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
+  else trsm_base_kernel<8><<<grid, TRSM_THREADS, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
   prof_end(st);
   UPDES_LAUNCH_CHECK();
   return 0;

@@ -73,7 +73,7 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   if (e == cudaSuccess) e = cudaMalloc(&h->sweep_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->sweep_err, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * n * 8);   // X and Y, 4 right-hand sides each
+  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * (n + 1) * 8);   // X and Y, 4 right-hand sides each (even stride)
   if (e != cudaSuccess) {
     updes_lu_destroy(h);
     return (int)e;

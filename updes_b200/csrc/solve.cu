@@ -23,18 +23,18 @@ constexpr int SOLVE_MAX_RHS = 4;
 
 // X = P (diag(scale) B): row equilibration factors (if any) are applied while gathering
 __global__ void gather_rows_kernel(const double *B, long long ldb, int nrhs, const int32_t *perm, long long n,
-                                   double *X, const double *scale) {
+                                   double *X, long long ldx, const double *scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int p = perm[i];
   const double sc = scale ? scale[p] : 1.0;
-  for (int f = 0; f < nrhs; f++) X[f * n + i] = B[f * ldb + p] * sc;
+  for (int f = 0; f < nrhs; f++) X[f * ldx + i] = B[f * ldb + p] * sc;
 }
 
-__global__ void copy_back_kernel(double *B, long long ldb, int nrhs, long long n, const double *X) {
+__global__ void copy_back_kernel(double *B, long long ldb, int nrhs, long long n, const double *X, long long ldx) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  for (int f = 0; f < nrhs; f++) B[f * ldb + i] = X[f * n + i];
+  for (int f = 0; f < nrhs; f++) B[f * ldb + i] = X[f * ldx + i];
 }
 
 // One block step of the substitution, fused in one launch.  Every CTA
@@ -590,6 +590,7 @@ struct Sweep2Params {
   int kb_begin, kb_end;         // block steps available in this factor
   int nblk;                     // ceil(n / 128)
   double *X, *Y;
+  long long ldx;                // stride between right-hand sides in X and Y (even when there is more than one)
   unsigned int *ticket;         // dynamic row-block counter (monotonic across launches)
   unsigned int ticket_base;
   int *err;
@@ -602,11 +603,11 @@ __device__ __forceinline__ double2 ld_relaxed_f64x2(const double *p) {
 }
 __device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == SW2_SENTINEL; }
 
-__global__ void fill_sentinel_kernel(double *Y, long long n, long long r0, long long cnt, int nrhs) {
+__global__ void fill_sentinel_kernel(double *Y, long long ldx, long long r0, long long cnt, int nrhs) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= cnt * nrhs) return;
   const long long f = t / cnt, c = t % cnt;
-  Y[f * n + r0 + c] = __longlong_as_double((long long)SW2_SENTINEL);
+  Y[f * ldx + r0 + c] = __longlong_as_double((long long)SW2_SENTINEL);
 }
 
 template <bool UPPER, int NR>
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nsteps = P.kb_end - P.kb_begin;
   const int nrowblocks = UPPER ? P.kb_end : P.nblk - P.kb_begin;
-  const long long n = P.n;
+  const long long n = P.n, ldx = P.ldx;
 
   while (true) {
     __syncthreads();                                       // previous block's shared state is dead
@@ -650,6 +651,14 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
           for (int c = lane; c < SB; c += 32)
             S.T[r * (SB + 1) + c] = (r < nbj && c < nbj) ? base[(long long)r * P.ld + c] : (r == c ? 1.0 : 0.0);
       }
+    }
+
+    // right-hand side of my rows, fetched now so that it is not on the critical path after the last tile
+    double xpre[NR];
+#pragma unroll
+    for (int f = 0; f < NR; f++) {
+      const int r = warp + lane * SW2_NW;
+      xpre[f] = (diag && lane < SW2_RW && r < nbj) ? P.X[(long long)f * ldx + r0 + r] : 0.0;
     }
 
     // ---- stream the row panel: acc[u][f] = partial sums of row (warp + u*NW) over my 4 columns per tile ----
@@ -696,7 +705,7 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
         unsigned int polls = 0;
 #pragma unroll
         for (int f = 0; f < NR; f++) {
-          const double *yb = P.Y + (long long)f * n + k0;
+          const double *yb = P.Y + (long long)f * ldx + k0;
           double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
           while (true) {
             bool ok = true;
@@ -747,8 +756,8 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
         for (int u = 1; u < SW2_RW; u++) mine = lane == u ? acc[u][f] : mine;
         const int r = warp + lane * SW2_NW;
         if (r < nbj) {
-          double *xp = P.X + (long long)f * n + r0 + r;
-          if (diag) S.xs[f][r] = *xp - mine;
+          double *xp = P.X + (long long)f * ldx + r0 + r;
+          if (diag) S.xs[f][r] = xpre[f] - mine;
           else *xp -= mine;
         } else if (diag) {
           S.xs[f][r] = 0.0;
@@ -792,7 +801,7 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
           }
           S.xs[f][base + lane] = x;
           // publish this sub-block at once: consumers poll the data itself
-          if (base + lane < nbj) __stcg(P.Y + (long long)f * n + r0 + base + lane, x);
+          if (base + lane < nbj) __stcg(P.Y + (long long)f * ldx + r0 + base + lane, x);
         }
       }
       __syncthreads();
@@ -835,17 +844,18 @@ static int launch_sweep2(UpdesLU *h, Sweep2Params &P, int grid, cudaStream_t st)
 // X is the running right-hand side (rows past the solved range are updated in place), Y receives the
 // solved blocks.  nrhs <= SOLVE_MAX_RHS.
 int tri_sweep_rowblock(UpdesLU *h, const double *LU, long long ld, long long n, bool upper, long long cbase,
-                       int kb_begin, int kb_end, double *X, double *Y, int nrhs, cudaStream_t st) {
+                       int kb_begin, int kb_end, double *X, double *Y, long long ldx, int nrhs, cudaStream_t st) {
   if (kb_end <= kb_begin) return 0;
+  if (nrhs > 1 && ((ldx & 1) || (((uintptr_t)X | (uintptr_t)Y) & 15))) return -9;   // 16-byte accesses to x blocks
   const int nblk = (int)((n + SB - 1) / SB);
   const long long y0 = 128LL * kb_begin;
   const long long ycnt = (128LL * kb_end < n ? 128LL * kb_end : n) - y0;
   const int nr = nrhs > 1 ? SOLVE_MAX_RHS : 1;
-  fill_sentinel_kernel<<<(unsigned)((ycnt * nr + 255) / 256), 256, 0, st>>>(Y, n, y0, ycnt, nr);
+  fill_sentinel_kernel<<<(unsigned)((ycnt * nr + 255) / 256), 256, 0, st>>>(Y, ldx, y0, ycnt, nr);
   UPDES_LAUNCH_CHECK();
   Sweep2Params P;
   P.LU = LU; P.ld = ld; P.n = n; P.cbase = cbase; P.kb_begin = kb_begin; P.kb_end = kb_end; P.nblk = nblk;
-  P.X = X; P.Y = Y; P.ticket = h->sweep_ticket; P.ticket_base = h->sweep_ticket_count; P.err = h->sweep_err;
+  P.X = X; P.Y = Y; P.ldx = ldx; P.ticket = h->sweep_ticket; P.ticket_base = h->sweep_ticket_count; P.err = h->sweep_err;
   const int nrowblocks = upper ? kb_end : nblk - kb_begin;
   const int grid = nrowblocks < h->num_sms ? nrowblocks : h->num_sms;
   h->sweep_ticket_count += (unsigned int)(nrowblocks + grid);      // every CTA draws one ticket past the end
@@ -927,9 +937,10 @@ static int solve_chunk(UpdesLU *h, const double *LU, double *X, double *Y, int n
     return tri_block_sweep(h->num_sms, LU, h->ld, n, true, 0, 0, n, Y, X, nrhs, st);
   }
   if (h->solve_variant == 2) {
-    int rc = tri_sweep_rowblock(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, nrhs, st);
+    const long long ldx = (n + 1) & ~1LL;
+    int rc = tri_sweep_rowblock(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, ldx, nrhs, st);
     if (rc) return rc;
-    return tri_sweep_rowblock(h, LU, h->ld, n, true, 0, 0, nblk, Y, X, nrhs, st);
+    return tri_sweep_rowblock(h, LU, h->ld, n, true, 0, 0, nblk, Y, X, ldx, nrhs, st);
   }
   int rc = tri_sweep_persistent(h, LU, h->ld, n, false, 0, 0, nblk, X, Y, nrhs, st);
   if (rc) return rc;
@@ -962,13 +973,15 @@ extern "C" int updes_lu_solve(UpdesLU *h, const double *LU, const int32_t *ipiv,
       UPDES_LAUNCH_CHECK();
       continue;
     }
-    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf, h->row_scale);
+    // the streaming sweeps read x blocks with 16-byte accesses: right-hand sides sit at an even stride there
+    const long long ldx = h->solve_variant == 2 ? ((n + 1) & ~1LL) : n;
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, h->perm, n, h->xbuf, ldx, h->row_scale);
     UPDES_LAUNCH_CHECK();
     prof_begin(PROF_SOLVE, 8.0 * (double)n * (double)n, st);
-    int rc = solve_chunk(h, LU, h->xbuf, h->xbuf + (size_t)SOLVE_MAX_RHS * n, nf, st);
+    int rc = solve_chunk(h, LU, h->xbuf, h->xbuf + (size_t)SOLVE_MAX_RHS * ldx, nf, st);
     prof_end(st);
     if (rc) return rc;
-    copy_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, n, h->xbuf);
+    copy_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Bf, ldb, nf, n, h->xbuf, ldx);
     UPDES_LAUNCH_CHECK();
   }
   return 0;
@@ -988,7 +1001,7 @@ extern "C" int updes_lu_permute_rhs(UpdesLU *h, const double *B, int64_t ldb, in
   if (ldb < h->n) return -3;
   if (!X) return -5;
   if (nrhs <= 0) return 0;
-  gather_rows_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, nrhs, h->perm, h->n, X, h->row_scale);
+  gather_rows_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, ldb, nrhs, h->perm, h->n, X, h->n, h->row_scale);
   UPDES_LAUNCH_CHECK();
   return 0;
 }
@@ -1015,9 +1028,9 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
   int rc;
   // the persistent kernel works on the 128-row partition of [0, n): the column block must be aligned to it
   const bool aligned = (r0 % SB) == 0 && ((width % SB) == 0 || r0 + width == n);
-  if (h->solve_variant == 2 && aligned && (nrhs == 1 || nrhs == SOLVE_MAX_RHS))
+  if (h->solve_variant == 2 && aligned && nrhs == 1)
     rc = tri_sweep_rowblock(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
-                            (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
+                            (int)((r0 + width + SB - 1) / SB), X, Y, n, nrhs, st);
   else if (h->solve_variant != 0 && aligned)
     rc = tri_sweep_persistent(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
                               (int)((r0 + width + SB - 1) / SB), X, Y, nrhs, st);
