@@ -432,18 +432,25 @@ def assemble_q(cloud, q_internal, boundary_arrays):
     return q
 
 
-def reference_solve(cloud, kind, param, max_degree, rowcoef, q, betas=None):
+def reference_solve(cloud, kind, param, max_degree, rowcoef, q, betas=None, timings=None):
     """The reference's linear algebra, literally (assembly.py:366-410, operators.py:602-616):
     B = (diffMat @ inv(A))[:, :N];  u = QR-solve(B, q);  coeffs = inv(A) @ [u; 0].
-    Returns (vals, coeffs, B)."""
+    Returns (vals, coeffs, B).  `timings` (a dict) receives the seconds spent assembling the two matrices
+    (O(n^2)) and in the dense linear algebra (O(n^3)), for bench.py's size extrapolation."""
+    import time
     import scipy.linalg as sla
     N = cloud.N
     M = compute_nb_monomials(max_degree, 2)
+    t0 = time.perf_counter()
     D = assemble_diffMat(cloud, kind, param, M, rowcoef, betas)
     A = assemble_A(cloud, kind, param, M)
+    t1 = time.perf_counter()
     inv_A = np.linalg.inv(A)                      # assembly.py:90
     B = (D @ inv_A)[:, :N]                        # assembly.py:399-401
     Q, R = sla.qr(B)                              # operators.py:612-613 (lineax QR)
     u = sla.solve_triangular(R, Q.T @ q)
     coeffs = inv_A @ np.concatenate([u, np.zeros(M)])   # assembly.py:404-410
+    if timings is not None:
+        timings["assemble_s"] = t1 - t0
+        timings["linalg_s"] = time.perf_counter() - t1
     return u, coeffs, B
