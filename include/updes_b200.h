@@ -195,6 +195,9 @@ int64_t updes_launch_count(void);
  * 0 trailing-update GEMM, 1 panel, 2 row interchanges, 3 triangular base solve, 4 assembly, 5 solve. */
 int updes_profile_enable(int on);
 int updes_profile_read(int cat, double *ms, double *work, int64_t *count);
+/* per-launch records of one class in launch order (ms[i], work[i], i < min(return value, max)); returns the number
+ * of records of the class, or a negative CUDA error code */
+int64_t updes_profile_records(int cat, double *ms, double *work, int64_t max);
 /* tuning hook: columns per thread of the assembly kernel (bit 0: closed-form Laplacian rows 4 instead of 2;
  * bit 1: general jets 2 instead of 4) */
 int updes_assemble_set_variant(int variant);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "updes_profile_enable": (_I32, [_I32]),
     "updes_assemble_set_variant": (_I32, [_I32]),
     "updes_profile_read": (_I32, [_I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    "updes_profile_records": (ctypes.c_int64, [_I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int64]),
 }
 
 _lib = None
@@ -118,3 +119,16 @@ def profile_read(name: str):
     check(load().updes_profile_read(PROF_CLASSES[name], ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt)),
           "updes_profile_read")
     return ms.value, work.value, cnt.value
+
+
+def profile_records(name: str, limit: int = 1 << 20):
+    """Per-launch (ms, work) arrays of one kernel class since profile_enable(True), in launch order."""
+    import numpy as np
+    ms = np.zeros(limit)
+    work = np.zeros(limit)
+    dp = ctypes.POINTER(ctypes.c_double)
+    cnt = int(load().updes_profile_records(PROF_CLASSES[name], ms.ctypes.data_as(dp), work.ctypes.data_as(dp), limit))
+    if cnt < 0:
+        raise RuntimeError("updes_profile_records failed: CUDA error %d" % -cnt)
+    cnt = min(cnt, limit)
+    return ms[:cnt], work[:cnt]

@@ -60,6 +60,8 @@ int panel_width_for(const UpdesLU *h, int64_t m);
 int lu_panel_base(UpdesLU *h, int v, int64_t r0, int64_t c0, int jb, int32_t *ipiv, int32_t *info, cudaStream_t st);
 int swap_rows(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t k0, int64_t npiv, const int32_t *ipiv,
               cudaStream_t st);
+int swap_rows_hole(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t hole0, int64_t holew, int64_t k0, int64_t npiv,
+                   const int32_t *ipiv, cudaStream_t st);
 // B <- L^-1 B, L = unit-lower n1 x n1 at (rl, cl) of view vl, B = n1 x ncols at (rb, cb) of view vb
 int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int vb, int64_t rb, int64_t cb,
                     int64_t ncols, cudaStream_t st);

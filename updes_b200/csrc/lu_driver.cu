@@ -26,9 +26,7 @@ int lu_recursive(UpdesLU *h, int v, int64_t r0, int64_t c0, int64_t nc, int64_t 
   if (nc <= W) {
     int rc = lu_panel_base(h, v, r0, c0, (int)nc, ipiv, info, st);
     if (rc) return rc;
-    rc = swap_rows(h, v, swap_lo, c0 - swap_lo, r0, nc, ipiv, st);
-    if (rc) return rc;
-    return swap_rows(h, v, c0 + nc, swap_hi - (c0 + nc), r0, nc, ipiv, st);
+    return swap_rows_hole(h, v, swap_lo, swap_hi - swap_lo, c0, nc, r0, nc, ipiv, st);   // left and right of the panel at once
   }
   int64_t n1;
   if (nc <= 16) n1 = 8;           // only reached when W == 8 (very tall panels)

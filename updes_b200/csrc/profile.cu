@@ -53,3 +53,21 @@ extern "C" int updes_profile_read(int cat, double *ms, double *work, int64_t *co
   if (count) *count = c;
   return 0;
 }
+
+// Per-launch records of class `cat` since the last enable, in launch order: ms[i], work[i] for i < min(count, max).
+// Returns the number of records of that class (or a negative CUDA error).
+extern "C" int64_t updes_profile_records(int cat, double *ms, double *work, int64_t max) {
+  using namespace updes;
+  int64_t c = 0;
+  for (auto &r : g_records) {
+    if (r.cat != cat) continue;
+    if (c < max) {
+      if (cudaEventSynchronize(r.b) != cudaSuccess) return -(int64_t)cudaGetLastError();
+      float f = 0; cudaEventElapsedTime(&f, r.a, r.b);
+      if (ms) ms[c] = f;
+      if (work) work[c] = r.work;
+    }
+    c++;
+  }
+  return c;
+}
