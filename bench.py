@@ -572,11 +572,19 @@ def _timeline_summary(dist, dlu, world):
     return out
 
 
-def _dist_pass(torch, dist, asm, be, dlu, rows, M, b):
+def _dist_pass(torch, dist, asm, be, dlu, rows, M, b, phases=None):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases is not None else None
+    if ev: ev[0].record()
     be.info.zero_()
     be.assemble(rows, "polyharmonic", 1.0, M)
+    if ev: ev[1].record()
     dlu.factor()
-    return dlu.solve(b)
+    if ev: ev[2].record()
+    x = dlu.solve(b)
+    if ev:
+        ev[3].record()
+        phases.append(ev)
+    return x
 
 
 def _dist_correctness(torch, dist, asm, be, rows, cloud, M, b, x, exact):
@@ -613,8 +621,10 @@ def run_gpu_arm_distributed(args, world, rank, local):
     b = be.vector(q)
     state = {}
 
+    phases = []
+
     def step():
-        state["x"] = _dist_pass(torch, dist, asm, be, dlu, rows, M, b)
+        state["x"] = _dist_pass(torch, dist, asm, be, dlu, rows, M, b, phases)
 
     def barrier():
         dist.barrier()
@@ -623,6 +633,7 @@ def run_gpu_arm_distributed(args, world, rank, local):
     for _ in range(args.warmup):
         step()
     barrier()
+    phases.clear()
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.profile_enable(True)
     l0 = _lib.launch_count()
@@ -640,6 +651,11 @@ def run_gpu_arm_distributed(args, world, rank, local):
     prof = {k: _lib.profile_read(k) for k in ("gemm", "panel", "swap", "trsm", "assemble")}
     _lib.profile_enable(False)
     value = lu_flops(n) / (ms_step * 1e-3) * 1e-12
+    # phase times on this rank's stream (CUDA events), mean over the timed steps, max over ranks
+    ph = torch.tensor([sum(e[i].elapsed_time(e[i + 1]) for e in phases) / max(len(phases), 1) for i in range(3)],
+                      device="cuda", dtype=torch.float64)
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    phase_ms = {"assemble": float(ph[0].item()), "lu": float(ph[1].item()), "solve": float(ph[2].item())}
 
     berr, max_err, status = _dist_correctness(torch, dist, asm, be, rows, cloud, M, b, state["x"], exact)
 
@@ -706,6 +722,7 @@ def run_gpu_arm_distributed(args, world, rank, local):
                              "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None,
                              "share_of_step": g_ms / (ms_step * args.steps), "peak_source": peak_src},
                 "breakdown": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] // max(args.steps, 1)} for k, v in prof.items()},
+                "phase_ms_per_step": phase_ms,
                 "per_gpu_tflops": value / world, "cpu_baseline": None, "timeline": timeline, "config5": config5,
                 "correctness": {"backward_error": berr, "max_err_vs_analytic": max_err, "zero_pivot": status}}
         print(json.dumps(line), flush=True)

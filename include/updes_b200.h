@@ -159,6 +159,9 @@ int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
  * ones in the grid-wide cooperative kernel; 1 = first-generation cluster + grid kernels; 0 = first-generation grid
  * kernel only */
 int updes_lu_set_panel_variant(UpdesLU *handle, int variant);
+/* tuning hook: largest block (rows: 32, 64, 96 or 128; default 128) of the unit-lower triangular solve
+ * U12 = L11^-1 A12 handled by one substitution kernel instead of recursion + small GEMMs */
+int updes_lu_set_trsm_base(UpdesLU *handle, int rows);
 /* triangular solves: 2 (default) = row-block streaming sweeps (one launch per direction, solved blocks published
  * through the data), 1 = step-synchronous persistent sweeps, 0 = one launch per 128-row block */
 int updes_lu_set_solve_variant(UpdesLU *handle, int variant);

@@ -13,14 +13,14 @@ from updes_b200.assembly import padded_ld
 from updes_b200.linalg import LUFactorization
 
 
-def model(n):
+def model(n, base=128):
     g = []
 
     def up32(x):
         return (x // 2 + 31) // 32 * 32
 
     def trsm_rec(n1, ncols):
-        if n1 <= 32:
+        if n1 <= base:
             return
         h = up32(n1)
         trsm_rec(h, ncols)
@@ -40,11 +40,12 @@ def model(n):
     return g
 
 
-def probe(n):
+def probe(n, base=128):
     gen = torch.Generator(device="cuda").manual_seed(n)
     A = torch.randn((n, padded_ld(n)), dtype=torch.float64, device="cuda", generator=gen)
     K = A.clone()
     lu = LUFactorization(K, n)
+    lu.set_trsm_base(base)
     lu.factor(); torch.cuda.synchronize()
     K.copy_(A)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -56,14 +57,14 @@ def probe(n):
     ms, work = _lib.profile_records("gemm")
     other = {k: _lib.profile_read(k) for k in ("panel", "swap", "trsm")}
     _lib.profile_enable(False)
-    shapes = model(n)
+    shapes = model(n, base)
     assert len(shapes) == len(ms), (len(shapes), len(ms))
     cls = defaultdict(lambda: [0, 0.0, 0.0])
     for (m, nn, k, w), t, fl in zip(shapes, ms, work):
         assert abs(2.0 * m * nn * k - fl) < 1, (m, nn, k, fl)
         c = cls[(w, k)]
         c[0] += 1; c[1] += t; c[2] += fl
-    out = {"n": n, "lu_ms_unprofiled": round(plain_ms, 2), "gemm_ms_profiled": round(float(ms.sum()), 2),
+    out = {"n": n, "trsm_base": base, "lu_ms_unprofiled": round(plain_ms, 2), "gemm_ms_profiled": round(float(ms.sum()), 2),
            "other": {k: [round(v[0], 2), v[2]] for k, v in other.items()}, "classes": []}
     for key in sorted(cls):
         c = cls[key]
@@ -74,4 +75,4 @@ def probe(n):
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [8192]
-    print(json.dumps([probe(n) for n in sizes]))
+    print(json.dumps([probe(n, b) for n in sizes for b in (128, 32)]))

@@ -47,6 +47,7 @@ SIGNATURES = {
     "updes_lu_set_panel_capacity": (_I32, [_VP, _I64]),
     "updes_lu_set_solve_variant": (_I32, [_VP, _I32]),
     "updes_lu_set_panel_variant": (_I32, [_VP, _I32]),
+    "updes_lu_set_trsm_base": (_I32, [_VP, _I32]),
     "updes_lu_panel_factor": (_I32, [_VP, _I32, _I64, _I64, _I64, _VP, _VP, _VP]),
     "updes_lu_apply_swaps": (_I32, [_VP, _I32, _I64, _I64, _I64, _I64, _VP, _VP]),
     "updes_lu_trsm": (_I32, [_VP, _I32, _I64, _I64, _I64, _I32, _I64, _I64, _I64, _VP]),

@@ -423,6 +423,15 @@ extern "C" int updes_lu_set_panel_capacity(UpdesLU *handle, int64_t rows) {
   return 0;
 }
 
+/* tuning hook: largest block (rows, multiple of 32, <= 128) of the unit-lower solve handled by one substitution
+ * kernel; 32 restores the first-generation recursion down to 32-row blocks */
+extern "C" int updes_lu_set_trsm_base(UpdesLU *handle, int rows) {
+  if (!handle) return -1;
+  if (rows < 32 || rows > 128 || (rows % 32)) return -2;
+  handle->trsm_base_rows = rows;
+  return 0;
+}
+
 extern "C" int updes_lu_set_panel_variant(UpdesLU *handle, int variant) {
   if (!handle) return -1;
   if (variant < 0 || variant > 2) return -2;

@@ -24,9 +24,11 @@ struct UpdesLU {
   int64_t panel_cap = 0;   // rows a 32-wide register-resident panel can hold (0 = num_sms * 640); test hook
   int panel_variant = 2;   // 2 (default): implicit-pivoting kernels (cluster push exchange for <= 8 192 rows, grid kernel above);
                            // 1: first-generation cluster + grid kernels; 0: first-generation grid kernel only
+  int trsm_base_rows = 128; // largest block of the triangular solve handled by one substitution kernel (32: first generation)
   int gemm_kdeep = 1;      // 1 (default): 32-deep pipeline stages (two 16-k sub-tiles per barrier round) when k % 32 == 0
   int gemm_variant = 1;    // 1 (default): ping-pong, two 128x64 CTAs per SM; 0: one 128x128 CTA per SM
   MatView view[UPDES_MAX_VIEWS];
+  void *workspace = nullptr;       // the one device allocation every pointer below points into
   // device workspace of the panel kernel
   double *cand = nullptr;          // [2][num_sms][PANEL_W] candidate pivot rows
   double *top = nullptr;           // [2][PANEL_W] row currently at the diagonal position

@@ -129,10 +129,69 @@ __global__ void __launch_bounds__(TRSM_THREADS) trsm_base_kernel(const double *L
   for (int i = 1; i < NB; i++) B[(rb + i) * ldb + c] = x[i];
 }
 
+// Base case for 32 < NB <= 128 (a multiple of 32): the same thread-per-column substitution, carried out in chunks of 32
+// rows.  The solved chunks of the CTA's 64 columns stay in shared memory next to L, so a chunk first takes the
+// contributions of all earlier chunks (independent FMAs, L broadcast from shared memory) and is then solved in
+// registers as above.  Replaces, per 128 rows, 4 launches of the 32-row kernel plus 3 tiny GEMM launches (k = 32, 64)
+// of the recursive solve: at n = 8192 those were 640 of the 1024 GEMM launches and 12 of 54 ms (29 ms with the base
+// launches), i.e. launch latency, not work.
+constexpr int TRSM_BIG = 128;
+constexpr int TRSM_BIG_SMEM = (TRSM_BIG * (TRSM_BIG + 1) + TRSM_BIG * TRSM_THREADS) * (int)sizeof(double);
+__global__ void __launch_bounds__(TRSM_THREADS) trsm_base_big_kernel(const double *Lm, long long ldl, long long rl, long long cl,
+                                                                     double *B, long long ldb, long long rb, long long cb,
+                                                                     long long ncols, int nb) {
+  extern __shared__ double trsm_sm[];
+  double *L = trsm_sm;                                   // [nb][TRSM_BIG + 1]
+  double *X = trsm_sm + TRSM_BIG * (TRSM_BIG + 1);       // [nb][TRSM_THREADS] solved rows of this CTA's columns
+  constexpr int LP = TRSM_BIG + 1;
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int i = t / nb, j = t - i * nb;
+    if (j < i) L[i * LP + j] = Lm[(rl + i) * ldl + cl + j];
+  }
+  __syncthreads();
+  const long long c = cb + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cb + ncols) return;
+  double *Xc = X + threadIdx.x;
+  for (int q0 = 0; q0 < nb; q0 += 32) {
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i] = B[(rb + q0 + i) * ldb + c];
+    const double *Lq = L + q0 * LP;
+    for (int j = 0; j < q0; j++) {                       // earlier chunks
+      const double xj = Xc[j * TRSM_THREADS];
+#pragma unroll
+      for (int i = 0; i < 32; i++) x[i] = fma(-Lq[i * LP + j], xj, x[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 31; j++) {                       // this chunk, column-oriented
+#pragma unroll
+      for (int i = j + 1; i < 32; i++) x[i] = fma(-Lq[i * LP + q0 + j], x[j], x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      if (q0 + i > 0) B[(rb + q0 + i) * ldb + c] = x[i];
+      Xc[(q0 + i) * TRSM_THREADS] = x[i];
+    }
+  }
+}
+
 static int trsm_base(UpdesLU *h, int vl, int64_t rl, int64_t cl, int nb, int vb, int64_t rb, int64_t cb,
                      int64_t ncols, cudaStream_t st) {
   const MatView &VL = h->view[vl], &VB = h->view[vb];
   const unsigned grid = (unsigned)((ncols + TRSM_THREADS - 1) / TRSM_THREADS);
+  if (nb > 32) {
+    if (nb > TRSM_BIG || (nb % 32)) return -4;
+    static bool attr = false;
+    if (!attr) {
+      UPDES_CUDA_TRY(cudaFuncSetAttribute(trsm_base_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_BIG_SMEM));
+      attr = true;
+    }
+    prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
+    trsm_base_big_kernel<<<grid, TRSM_THREADS, TRSM_BIG_SMEM, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols, nb);
+    prof_end(st);
+    UPDES_LAUNCH_CHECK();
+    return 0;
+  }
   if (nb != 32 && nb != 16 && nb != 8) return -4;
   prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
   if (nb == 32) trsm_base_kernel<32><<<grid, TRSM_THREADS, 0, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols);
@@ -149,7 +208,8 @@ int trsm_unit_lower(UpdesLU *h, int vl, int64_t rl, int64_t cl, int64_t n1, int 
                     int64_t ncols, cudaStream_t st) {
   if (n1 <= 0 || ncols <= 0) return 0;
   if (!h->view[vl].ptr || !h->view[vb].ptr) return -2;
-  if (n1 <= 32) return trsm_base(h, vl, rl, cl, (int)n1, vb, rb, cb, ncols, st);
+  if (n1 <= 32 || (h->trsm_base_rows >= n1 && n1 <= TRSM_BIG && (n1 % 32) == 0))
+    return trsm_base(h, vl, rl, cl, (int)n1, vb, rb, cb, ncols, st);
   const int64_t hlf = (n1 / 2 + 31) / 32 * 32;
   int rc = trsm_unit_lower(h, vl, rl, cl, hlf, vb, rb, cb, ncols, st);
   if (rc) return rc;

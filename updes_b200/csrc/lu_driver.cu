@@ -54,36 +54,44 @@ extern "C" int updes_lu_create(UpdesLU **handle, int64_t n, int64_t ld) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  // ONE device allocation for the whole workspace (cudaMalloc / cudaFree synchronise the device and cost ~0.1-1 ms
+  // each: eleven of them were a visible share of a small factorisation), carved at 256-byte boundaries
   const size_t W = updes::PANEL_W;
-  if (e == cudaSuccess) e = cudaMalloc(&h->cand, sizeof(double) * 2 * h->num_sms * W);
-  if (e == cudaSuccess) e = cudaMalloc(&h->top, sizeof(double) * 2 * W);
-  if (e == cudaSuccess) e = cudaMalloc(&h->candval, sizeof(double) * 2 * h->num_sms);
-  if (e == cudaSuccess) e = cudaMalloc(&h->candrow, sizeof(int32_t) * 2 * h->num_sms);
-  if (e == cudaSuccess) e = cudaMalloc(&h->barrier, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->barrier, 0, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->gemm_counters, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
-  if (e == cudaSuccess) e = cudaMemset(h->gemm_counters, 0, sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
   const size_t nflags = (size_t)((n + 127) / 128) + 1;
-  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_flags, sizeof(unsigned int) * nflags);
-  if (e == cudaSuccess) e = cudaMemset(h->sweep_flags, 0, sizeof(unsigned int) * nflags);
-  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_ticket, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->sweep_ticket, 0, sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->sweep_err, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(h->sweep_err, 0, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * n);
-  if (e == cudaSuccess) e = cudaMalloc(&h->xbuf, sizeof(double) * (n + 1) * 8);   // X and Y, 4 right-hand sides each (even stride)
+  size_t off = 0;
+  auto carve = [&off](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_cand = carve(sizeof(double) * 2 * h->num_sms * W);
+  const size_t o_top = carve(sizeof(double) * 2 * W);
+  const size_t o_candval = carve(sizeof(double) * 2 * h->num_sms);
+  const size_t o_candrow = carve(sizeof(int32_t) * 2 * h->num_sms);
+  const size_t o_barrier = carve(sizeof(unsigned int));
+  const size_t o_counters = carve(sizeof(unsigned int) * UPDES_GEMM_COUNTERS);
+  const size_t o_flags = carve(sizeof(unsigned int) * nflags);
+  const size_t o_ticket = carve(sizeof(unsigned int));
+  const size_t o_err = carve(sizeof(int));
+  const size_t zero_bytes = off;                       // everything above starts at zero
+  const size_t o_perm = carve(sizeof(int32_t) * n);
+  const size_t o_xbuf = carve(sizeof(double) * (n + 1) * 8);   // X and Y, 4 right-hand sides each (even stride)
+  char *base = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&base, off);
+  if (e == cudaSuccess) e = cudaMemset(base, 0, zero_bytes);
   if (e != cudaSuccess) {
-    updes_lu_destroy(h);
+    delete h;
     return (int)e;
   }
+  h->workspace = base;
+  h->cand = (double *)(base + o_cand); h->top = (double *)(base + o_top); h->candval = (double *)(base + o_candval);
+  h->candrow = (int32_t *)(base + o_candrow); h->barrier = (unsigned int *)(base + o_barrier);
+  h->gemm_counters = (unsigned int *)(base + o_counters); h->sweep_flags = (unsigned int *)(base + o_flags);
+  h->sweep_ticket = (unsigned int *)(base + o_ticket); h->sweep_err = (int *)(base + o_err);
+  h->perm = (int32_t *)(base + o_perm); h->xbuf = (double *)(base + o_xbuf);
   *handle = h;
   return 0;
 }
 
 extern "C" int updes_lu_destroy(UpdesLU *h) {
   if (!h) return 0;
-  cudaFree(h->cand); cudaFree(h->top); cudaFree(h->candval); cudaFree(h->candrow);
-  cudaFree(h->barrier); cudaFree(h->perm); cudaFree(h->xbuf); cudaFree(h->gemm_counters); cudaFree(h->sweep_flags); cudaFree(h->sweep_err); cudaFree(h->sweep_ticket);
+  cudaFree(h->workspace);
   delete h;
   return 0;
 }

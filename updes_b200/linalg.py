@@ -78,6 +78,9 @@ class LUFactorization:
     def set_panel_variant(self, variant: int):
         _lib.check(self._lib.updes_lu_set_panel_variant(self._handle, variant), "updes_lu_set_panel_variant")
 
+    def set_trsm_base(self, rows: int):
+        _lib.check(self._lib.updes_lu_set_trsm_base(self._handle, rows), "updes_lu_set_trsm_base")
+
     def set_solve_variant(self, variant: int):
         _lib.check(self._lib.updes_lu_set_solve_variant(self._handle, variant), "updes_lu_set_solve_variant")
 
