@@ -85,3 +85,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(UpdesEvalJets, EvalJetsImpl,
                                   .Attr<int32_t>("kind").Attr<double>("param").Attr<int32_t>("M")
                                   .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>());
+
+// Plain C helper for the Python side: size of the workspace result buffer UpdesEvalJets needs.
+extern "C" size_t UpdesEvalJetsWorkspaceBytes(int N, int npts, int nf) { return updes_eval_jets_workspace_bytes(N, npts, nf); }
