@@ -152,7 +152,8 @@ int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t 
 /* cap the persistent GEMM grid (0 = one CTA per SM) so NCCL kernels can run beside the update */
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule, bit 0: 1 = ping-pong (two 128x64 CTAs per SM), 0 = one 128x128 CTA per SM;
- * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round) */
+ * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round); bits 2-5: distance (in pipeline stages) of
+ * the producer's L2-only TMA prefetch, 0 = off; bits 6-7: operands it covers (1 = left tiles, 2 = right tiles) */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
 /* base panels: 2 (default) = implicit-pivoting kernels -- panels of <= 8 192 rows run in one thread-block cluster
  * whose CTAs push their candidates into each other's shared memory (one split cluster barrier per column), taller
@@ -187,6 +188,14 @@ int updes_lu_set_pivots(UpdesLU *handle, const int32_t *ipiv, void *stream);
 int updes_lu_permute_rhs(UpdesLU *handle, const double *B, int64_t ldb, int nrhs, double *X, void *stream);
 int updes_tri_block_sweep(UpdesLU *handle, int slot, int upper, int64_t r0, int64_t c0, int64_t width,
                           double *X, int nrhs, void *stream);
+/* left-looking distributed substitution (updes_b200/distributed.py): every rank forms the partial products of one
+ * row block against the solution entries it owns, out[i] = sum_{c_lo <= c < c_hi} A[r0+i][c] x[c] (x indexed by LOCAL
+ * column; an empty range writes zeros), the partials are summed on the block's owner, which then solves ONLY the
+ * width x width diagonal block in place on X[r0 .. r0+width) (upper = 0: unit lower, 1: upper with diagonal) */
+int updes_block_gemv(UpdesLU *handle, int slot, int64_t r0, int64_t nrows, int64_t c_lo, int64_t c_hi,
+                     const double *x, double *out, void *stream);
+int updes_tri_diag_solve(UpdesLU *handle, int slot, int upper, int64_t r0, int64_t c0, int64_t width, double *X,
+                         void *stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char *updes_b200_version(void);

@@ -113,5 +113,20 @@ class NumpyBackend:
             xv[r0:r0 + w] = np.linalg.solve(np.triu(T), xv[r0:r0 + w])
             xv[:r0] -= self.local[:r0, lc:lc + w] @ xv[r0:r0 + w]
 
+    def block_gemv(self, r0, w, c_lo, c_hi, xl, out):
+        self.calls.append(("gemv", r0, w, c_lo, c_hi))
+        if c_hi <= c_lo:
+            out.zero_()
+        else:
+            out.numpy()[:] = self.local[r0:r0 + w, c_lo:c_hi] @ xl.numpy()[c_lo:c_hi]
+
+    def diag_solve(self, upper, r0, lc, w, x):
+        xv = x.numpy()
+        T = self.local[r0:r0 + w, lc:lc + w]
+        xv[r0:r0 + w] = np.linalg.solve(np.triu(T) if upper else np.tril(T, -1) + np.eye(w), xv[r0:r0 + w])
+
+    def zeros(self, k):
+        return torch.zeros(k, dtype=torch.float64)
+
     def zero_pivot(self):
         return self.info

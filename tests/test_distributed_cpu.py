@@ -33,6 +33,8 @@ def _worker(rank, world, port, n, nb, seed, out):
         be.fill_from_global(K)
         lu = DistributedLU(layout, rank, be).factor()
         x = lu.solve(b).numpy().copy()
+        lu.solve_variant = "right"                       # first-generation column sweep: a second opinion
+        x_right = lu.solve(b).numpy().copy()
         # gather the factored column blocks on rank 0
         pieces = [None] * world
         dist.all_gather_object(pieces, (be.local[:, :be.cols].copy(), be.ipiv.copy(), be.calls))
@@ -42,7 +44,7 @@ def _worker(rank, world, port, n, nb, seed, out):
                 for j in layout.local_blocks(r):
                     w, lc = layout.width(j), layout.local_offset(j)
                     F[:, j * nb:j * nb + w] = loc[:, lc:lc + w]
-            np.savez(out, F=F, ipiv=pieces[0][1], x=x, K=K, b=b, same_piv=all(np.array_equal(p[1], pieces[0][1]) for p in pieces),
+            np.savez(out, F=F, ipiv=pieces[0][1], x=x, x_right=x_right, K=K, b=b, same_piv=all(np.array_equal(p[1], pieces[0][1]) for p in pieces),
                      panels_r1=np.array([c[1] for c in pieces[1][2] if c[0] == "panel"]))
     finally:
         dist.destroy_process_group()
@@ -59,6 +61,7 @@ def test_block_cyclic_lu_matches_lapack(tmp_path, world, n, nb):
     assert np.array_equal(r["ipiv"], piv)
     assert np.allclose(r["F"], lu, rtol=1e-10, atol=1e-10)
     assert np.allclose(r["x"], np.linalg.solve(r["K"], r["b"]), rtol=1e-8, atol=1e-8)
+    assert np.allclose(r["x_right"], r["x"], rtol=1e-9, atol=1e-10)      # left-looking and column-sweep solves agree
     # rank 1 factored exactly its own panels (global blocks 1, 1+world, ...)
     assert [int(v) // nb for v in r["panels_r1"]] == list(range(1, (n + nb - 1) // nb, world))
 

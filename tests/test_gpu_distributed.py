@@ -62,6 +62,10 @@ def _worker(rank, world, port, nx, nb, out):
         lu = DistributedLU(layout, rank, be).factor()
         bvec = torch.randn(n1, generator=g, dtype=torch.float64)
         x = lu.solve(bvec.numpy())
+        lu.solve_variant = "right"                       # first-generation column sweep as a second opinion
+        x_right = lu.solve(bvec.numpy())
+        lu.solve_variant = "left"
+        solves_agree = float((x - x_right).abs().max() / x.abs().max())
         lu_ref, piv_ref = torch.linalg.lu_factor(A)
         F = _gather_factors(layout, be, world, n1, nb)
         piv_same = bool(np.array_equal(be.ipiv.cpu().numpy(), piv_ref.numpy() - 1))
@@ -95,7 +99,7 @@ def _worker(rank, world, port, nx, nb, out):
         berr = float((Kfull @ x - bq).abs().max() / (Kfull.abs().sum(dim=1).max() * x.abs().max() + bq.abs().max()))
         res = [None] * world
         dist.all_gather_object(res, (float(piv_same), fac_err, sol_err, float(zp), float(asm_same), rec_err, lmax, berr,
-                                     float(be.zero_pivot())))
+                                     float(be.zero_pivot()), solves_agree))
         if rank == 0:
             np.save(out, np.array(res))
     finally:
@@ -119,6 +123,7 @@ def _run(world, nx, nb, tmp_path):
     assert np.all(r[:, 6] <= 1.0 + 1e-12), r    # partial pivoting: |L| <= 1
     assert np.all(r[:, 7] <= 1e-14), r          # backward error of the distributed solve
     assert np.all(r[:, 8] == 0)
+    assert np.all(r[:, 9] <= 1e-10), r          # left-looking solve == column-sweep solve (well-conditioned matrix)
 
 
 @pytest.mark.parametrize("nx,nb", [(24, 64), (40, 128), (50, 512)])

@@ -232,3 +232,67 @@ def test_lu_singular_reports_info():
     K[:, 40] = 0.0                                    # an exactly zero column -> zero pivot at column 41
     lu = LUFactorization(K, n).factor()
     assert lu.zero_pivot() == 41
+
+
+@pytest.mark.parametrize("variant", [1, 3, 3 | (4 << 2) | (3 << 6), 3 | (2 << 2) | (1 << 6), 1 | (8 << 2) | (2 << 6)])
+def test_dgemm_l2_prefetch_does_not_change_results(variant):
+    """The producer's L2-only TMA prefetch (distance / operand mask in the variant bits) is a pure hint."""
+    import torch
+    from updes_b200.linalg import LUFactorization
+    size, k = 3072, 512
+    _, K = _matrix(size, seed=11)
+    ref = K.clone()
+    ref[k:, k:size] -= ref[k:, :k] @ ref[:k, k:size]
+    lu = LUFactorization(K, size)
+    lu.set_gemm_variant(variant)
+    lu.gemm_sub(k, k, k, 0, 0, k, size - k, size - k, k)
+    torch.cuda.synchronize()
+    assert (K - ref).abs().max().item() <= 1e-12 * k * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("n,r0,w,c_lo,c_hi", [(1000, 128, 128, 0, 128), (1000, 256, 100, 0, 991), (2051, 1024, 512, 512, 2051),
+                                            (2051, 2048, 3, 64, 2048), (700, 0, 64, 0, 0), (5000, 1024, 1024, 0, 4096)])
+def test_block_gemv_partial_products(n, r0, w, c_lo, c_hi):
+    """updes_block_gemv: out = A[r0:r0+w, c_lo:c_hi] @ x[c_lo:c_hi] (the left-looking distributed substitution's partials)."""
+    import ctypes
+    import torch
+    from updes_b200 import _lib
+    from updes_b200.linalg import LUFactorization
+    A, K = _matrix(n, seed=n + w)
+    lu = LUFactorization(K, n)
+    lib = _lib.load()
+    _lib.check(lib.updes_lu_bind(lu._handle, 0, K.data_ptr(), n, K.shape[1]), "bind")
+    x = torch.randn(K.shape[1], dtype=torch.float64, device="cuda")
+    out = torch.full((w,), 7.0, dtype=torch.float64, device="cuda")
+    _lib.check(lib.updes_block_gemv(lu._handle, 0, r0, w, c_lo, c_hi, x.data_ptr(), out.data_ptr(), _lib.stream_ptr()), "gemv")
+    ref = K[r0:r0 + w, c_lo:c_hi] @ x[c_lo:c_hi]
+    scale = float((K[r0:r0 + w, c_lo:c_hi].abs() @ x[c_lo:c_hi].abs()).max()) if c_hi > c_lo else 1.0
+    assert float((out - ref).abs().max()) <= 1e-14 * max(scale, 1.0)
+    # argument validation through the ABI: odd first column, range past the leading dimension
+    assert lib.updes_block_gemv(lu._handle, 0, r0, w, 1, 8, x.data_ptr(), out.data_ptr(), _lib.stream_ptr()) == -5
+    assert lib.updes_block_gemv(lu._handle, 0, n, 1, 0, 8, x.data_ptr(), out.data_ptr(), _lib.stream_ptr()) == -3
+
+
+@pytest.mark.parametrize("n,r0,w", [(1024, 0, 1024), (2051, 1024, 1027), (1000, 256, 512), (1000, 64, 96), (3000, 2944, 56), (600, 128, 32)])
+@pytest.mark.parametrize("upper", [0, 1])
+def test_tri_diag_solve_touches_only_its_block(n, r0, w, upper):
+    """updes_tri_diag_solve: the w x w diagonal block at (r0, c0) solved in place on x[r0:r0+w]; nothing else moves.
+    The block sits at local column c0 != r0, as on a rank that owns only some of the column blocks."""
+    import torch
+    from updes_b200 import _lib
+    from updes_b200.linalg import LUFactorization
+    A, K = _matrix(n, seed=3 * n + w, dominant=True)
+    lu = LUFactorization(K, n)
+    lib = _lib.load()
+    _lib.check(lib.updes_lu_bind(lu._handle, 0, K.data_ptr(), n, K.shape[1]), "bind")
+    c0 = min((r0 // 2 + 64) & ~1, (K.shape[1] - w) & ~1)
+    T = K[r0:r0 + w, c0:c0 + w]
+    x = torch.randn(n, dtype=torch.float64, device="cuda")
+    x0 = x.clone()
+    _lib.check(lib.updes_tri_diag_solve(lu._handle, 0, upper, r0, c0, w, x.data_ptr(), _lib.stream_ptr()), "diag_solve")
+    Tm = torch.triu(T) if upper else torch.tril(T, -1) + torch.eye(w, dtype=torch.float64, device="cuda")
+    ref = torch.linalg.solve_triangular(Tm, x0[r0:r0 + w, None], upper=bool(upper))[:, 0]
+    assert float((x[r0:r0 + w] - ref).abs().max() / ref.abs().max()) <= 1e-11
+    keep = torch.ones(n, dtype=torch.bool, device="cuda"); keep[r0:r0 + w] = False
+    assert torch.equal(x[keep], x0[keep])
+    assert lu.check() == 0

@@ -55,6 +55,8 @@ SIGNATURES = {
     "updes_lu_set_pivots": (_I32, [_VP, _VP, _VP]),
     "updes_lu_permute_rhs": (_I32, [_VP, _VP, _I64, _I32, _VP, _VP]),
     "updes_tri_block_sweep": (_I32, [_VP, _I32, _I32, _I64, _I64, _I64, _VP, _I32, _VP]),
+    "updes_block_gemv": (_I32, [_VP, _I32, _I64, _I64, _I64, _I64, _VP, _VP, _VP]),
+    "updes_tri_diag_solve": (_I32, [_VP, _I32, _I32, _I64, _I64, _I64, _VP, _VP]),
     "updes_b200_version": (ctypes.c_char_p, []),
     "updes_launch_count": (_I64, []),
     "updes_profile_enable": (_I32, [_I32]),

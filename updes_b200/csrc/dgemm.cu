@@ -33,6 +33,8 @@ struct GemmParams {
   long long m, n, k;
   unsigned int *counter;       // dynamic tile scheduler: next tile index of THIS launch (starts at 0)
   unsigned int *next_counter;  // counter of the next launch on the stream, reset by this one
+  int pf_dist;                 // L2 prefetch distance in pipeline stages (0 = off)
+  int pf_mask;                 // 1: left-operand tiles, 2: right-operand tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +66,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// L2-only prefetch of a TMA box: the first CTA to touch a line otherwise pays the HBM latency inside its 2-stage ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -173,6 +179,17 @@ dgemm_sub_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
       for (int g = 0; g < BN / 16; g++)
         tma_load_2d(sa + Cfg::A_BYTES + g * 2048, &mapB, bcol + 16 * g, (int)(P.rb + kk), full);
+    }
+    if (P.pf_dist > 0 && p_kt + P.pf_dist < ktiles) {
+#pragma unroll
+      for (int ks = 0; ks < KSUB; ks++) {
+        const int kk = ((p_kt + P.pf_dist) * KSUB + ks) * GEMM_BK;
+        if (P.pf_mask & 1) tma_prefetch_2d(&mapA, (int)(P.ca + kk), arow);
+        if (P.pf_mask & 2) {
+#pragma unroll
+          for (int g = 0; g < BN / 16; g++) tma_prefetch_2d(&mapB, bcol + 16 * g, (int)(P.rb + kk));
+        }
+      }
     }
     if (++p_stage == Cfg::STAGES) { p_stage = 0; p_phase ^= 1; }
     if (++p_kt == ktiles) p_kt = 0;
@@ -352,6 +369,7 @@ static int launch_gemm(UpdesLU *h, const MatView &VA, const MatView &VB, const G
   Q.counter = h->gemm_counters + (h->gemm_launch_id % UPDES_GEMM_COUNTERS);
   Q.next_counter = h->gemm_counters + ((h->gemm_launch_id + 1) % UPDES_GEMM_COUNTERS);
   h->gemm_launch_id++;
+  Q.pf_dist = h->gemm_pf_dist; Q.pf_mask = h->gemm_pf_mask;
   prof_begin(PROF_GEMM, 2.0 * (double)P.m * (double)P.n * (double)P.k, st);
   dgemm_sub_kernel<BN, NW, KSUB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(VA.mapA, VB.mapB, Q);
   prof_end(st);
@@ -408,9 +426,11 @@ extern "C" int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas) {
 
 extern "C" int updes_lu_set_gemm_variant(UpdesLU *handle, int variant) {
   if (!handle) return -1;
-  if (variant < 0 || variant > 3) return -2;
+  if (variant < 0 || variant > 0x3ff) return -2;
   handle->gemm_variant = variant & 1;      // bit 0: ping-pong schedule
   handle->gemm_kdeep = (variant >> 1) & 1; // bit 1: 32-deep pipeline stages
+  handle->gemm_pf_dist = (variant >> 2) & 15;  // bits 2-5: L2 prefetch distance in pipeline stages (0 = off)
+  handle->gemm_pf_mask = (variant >> 6) & 3;   // bits 6-7: 1 = left-operand tiles, 2 = right-operand tiles
   return 0;
 }
 

@@ -594,6 +594,7 @@ struct Sweep2Params {
   unsigned int *ticket;         // dynamic row-block counter (monotonic across launches)
   unsigned int ticket_base;
   int *err;
+  int diag_only;                // 1: only the row blocks of the column block itself (no update of the rows beyond it)
 };
 
 __device__ __forceinline__ double2 ld_relaxed_f64x2(const double *p) {
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(SW2_THREADS, 1) tri_sweep2_kernel(Sweep2Params
   Sw2Smem<NR> &S = *reinterpret_cast<Sw2Smem<NR> *>(sw2_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nsteps = P.kb_end - P.kb_begin;
-  const int nrowblocks = UPPER ? P.kb_end : P.nblk - P.kb_begin;
+  const int nrowblocks = P.diag_only ? nsteps : (UPPER ? P.kb_end : P.nblk - P.kb_begin);
   const long long n = P.n, ldx = P.ldx;
 
   while (true) {
@@ -844,7 +845,8 @@ static int launch_sweep2(UpdesLU *h, Sweep2Params &P, int grid, cudaStream_t st)
 // X is the running right-hand side (rows past the solved range are updated in place), Y receives the
 // solved blocks.  nrhs <= SOLVE_MAX_RHS.
 int tri_sweep_rowblock(UpdesLU *h, const double *LU, long long ld, long long n, bool upper, long long cbase,
-                       int kb_begin, int kb_end, double *X, double *Y, long long ldx, int nrhs, cudaStream_t st) {
+                       int kb_begin, int kb_end, double *X, double *Y, long long ldx, int nrhs, cudaStream_t st,
+                       bool diag_only = false) {
   if (kb_end <= kb_begin) return 0;
   if (nrhs > 1 && ((ldx & 1) || (((uintptr_t)X | (uintptr_t)Y) & 15))) return -9;   // 16-byte accesses to x blocks
   const int nblk = (int)((n + SB - 1) / SB);
@@ -856,7 +858,8 @@ int tri_sweep_rowblock(UpdesLU *h, const double *LU, long long ld, long long n, 
   Sweep2Params P;
   P.LU = LU; P.ld = ld; P.n = n; P.cbase = cbase; P.kb_begin = kb_begin; P.kb_end = kb_end; P.nblk = nblk;
   P.X = X; P.Y = Y; P.ldx = ldx; P.ticket = h->sweep_ticket; P.ticket_base = h->sweep_ticket_count; P.err = h->sweep_err;
-  const int nrowblocks = upper ? kb_end : nblk - kb_begin;
+  P.diag_only = diag_only ? 1 : 0;
+  const int nrowblocks = diag_only ? kb_end - kb_begin : (upper ? kb_end : nblk - kb_begin);
   const int grid = nrowblocks < h->num_sms ? nrowblocks : h->num_sms;
   h->sweep_ticket_count += (unsigned int)(nrowblocks + grid);      // every CTA draws one ticket past the end
   if (nr == 1) return upper ? launch_sweep2<true, 1>(h, P, grid, st) : launch_sweep2<false, 1>(h, P, grid, st);
@@ -882,7 +885,8 @@ static int step_grid(int num_sms, long long rows) {
 // Forward (unit lower): rows below r0 of X are the running right-hand side; the solved block goes to Y.
 // Backward (upper): same upwards.  X and Y are full-length [nrhs][n] vectors (X != Y).
 int tri_block_sweep(int num_sms, const double *LU, long long ld, long long n, bool upper, long long r0, long long c0,
-                    long long w, double *X, double *Y, int nrhs, cudaStream_t st) {
+                    long long w, double *X, double *Y, int nrhs, cudaStream_t st, bool diag_only = false) {
+  const long long row_lo = diag_only ? r0 : 0, row_hi = diag_only ? r0 + w : n;   // rows whose X may be updated
   int rc = ensure_solve_attrs();
   if (rc) return rc;
   const long long nsub = (w + SB - 1) / SB;
@@ -892,11 +896,11 @@ int tri_block_sweep(int num_sms, const double *LU, long long ld, long long n, bo
     const int nb = (int)((w - s * SB) < SB ? (w - s * SB) : SB);
     if (!upper) {
       const long long i0 = k0 + nb;
-      tri_step_kernel<false><<<step_grid(num_sms, n - i0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, i0, n, X,
-                                                                                         Y, nrhs);
+      tri_step_kernel<false><<<step_grid(num_sms, row_hi - i0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, i0,
+                                                                                              row_hi, X, Y, nrhs);
     } else {
-      tri_step_kernel<true><<<step_grid(num_sms, k0), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, 0, k0, X, Y,
-                                                                                     nrhs);
+      tri_step_kernel<true><<<step_grid(num_sms, k0 - row_lo), STEP_THREADS, STEP_SMEM, st>>>(LU, ld, n, k0, cc, nb, row_lo,
+                                                                                             k0, X, Y, nrhs);
     }
     UPDES_LAUNCH_CHECK();
   }
@@ -1038,6 +1042,101 @@ extern "C" int updes_tri_block_sweep(UpdesLU *h, int slot, int upper, int64_t r0
     rc = tri_block_sweep(h->num_sms, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, r0, c0, width, X, Y, nrhs, st);
   if (rc) return rc;
   copy_block_kernel<<<(unsigned)((width * nrhs + 255) / 256), 256, 0, st>>>(X, Y, n, r0, width, nrhs);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- left-looking distributed substitution: partial products + diagonal-block solves ---------------------------
+// out[i] = sum_{c in [c_lo, c_hi)} A[r0 + i][c] * x[c]: one CTA per row, the row segment is contiguous in the row-major
+// local matrix (16-byte loads, four per thread in flight); HBM-read bound, (c_hi - c_lo) * 8 bytes per row.
+namespace updes {
+constexpr int GEMV_THREADS = 128;
+__global__ void __launch_bounds__(GEMV_THREADS) block_gemv_kernel(const double *__restrict__ A, long long ld, long long r0,
+                                                                  long long c_lo, long long c_hi,
+                                                                  const double *__restrict__ x, double *__restrict__ out) {
+  const double *row = A + (r0 + blockIdx.x) * ld;
+  const int tid = threadIdx.x;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  const long long c_even = c_lo + ((c_hi - c_lo) & ~1LL);          // c_lo is even (caller checks): 16-byte aligned pairs
+  long long c = c_lo + 2 * tid;
+  for (; c + 6 * GEMV_THREADS < c_even; c += 8 * GEMV_THREADS) {
+    const double2 a0 = *reinterpret_cast<const double2 *>(row + c), a1 = *reinterpret_cast<const double2 *>(row + c + 2 * GEMV_THREADS);
+    const double2 a2 = *reinterpret_cast<const double2 *>(row + c + 4 * GEMV_THREADS), a3 = *reinterpret_cast<const double2 *>(row + c + 6 * GEMV_THREADS);
+    const double2 x0 = *reinterpret_cast<const double2 *>(x + c), x1 = *reinterpret_cast<const double2 *>(x + c + 2 * GEMV_THREADS);
+    const double2 x2 = *reinterpret_cast<const double2 *>(x + c + 4 * GEMV_THREADS), x3 = *reinterpret_cast<const double2 *>(x + c + 6 * GEMV_THREADS);
+    acc0 = fma(a0.y, x0.y, fma(a0.x, x0.x, acc0)); acc1 = fma(a1.y, x1.y, fma(a1.x, x1.x, acc1));
+    acc2 = fma(a2.y, x2.y, fma(a2.x, x2.x, acc2)); acc3 = fma(a3.y, x3.y, fma(a3.x, x3.x, acc3));
+  }
+  for (; c < c_even; c += 2 * GEMV_THREADS) {
+    const double2 a0 = *reinterpret_cast<const double2 *>(row + c);
+    const double2 x0 = *reinterpret_cast<const double2 *>(x + c);
+    acc0 = fma(a0.y, x0.y, fma(a0.x, x0.x, acc0));
+  }
+  if (tid == 0 && c_even < c_hi) acc1 = fma(row[c_even], x[c_even], acc1);
+  double v = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __shared__ double part[GEMV_THREADS / 32];
+  if ((tid & 31) == 0) part[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < GEMV_THREADS / 32; w++) t += part[w];
+    out[blockIdx.x] = t;
+  }
+}
+}  // namespace updes
+
+/* out[i] = sum_{c_lo <= c < c_hi} A[r0+i][c] x[c] for i < nrows, A = the buffer bound to `slot`; x is indexed by the
+ * LOCAL column (length >= c_hi); an empty column range writes zeros */
+extern "C" int updes_block_gemv(UpdesLU *h, int slot, int64_t r0, int64_t nrows, int64_t c_lo, int64_t c_hi,
+                                const double *x, double *out, void *stream) {
+  using namespace updes;
+  if (!h) return -1;
+  if (slot < 0 || slot >= UPDES_MAX_VIEWS || !h->view[slot].ptr) return -2;
+  if (r0 < 0 || nrows < 0 || r0 + nrows > h->view[slot].rows) return -3;
+  if (c_lo < 0 || (c_lo & 1) || c_hi > h->view[slot].ld) return -5;
+  if (!x || (((uintptr_t)x) & 15)) return -7;
+  if (!out) return -8;
+  if (nrows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c_hi <= c_lo) {
+    UPDES_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nrows, st));
+    return 0;
+  }
+  prof_begin(PROF_SOLVE, 8.0 * (double)nrows * (double)(c_hi - c_lo), st);
+  block_gemv_kernel<<<(unsigned)nrows, GEMV_THREADS, 0, st>>>(h->view[slot].ptr, h->view[slot].ld, r0, c_lo, c_hi, x, out);
+  prof_end(st);
+  UPDES_LAUNCH_CHECK();
+  return 0;
+}
+
+/* Solve ONLY the width x width triangular diagonal block at rows [r0, r0+width), columns [c0, c0+width) of `slot`,
+ * in place on X[r0 .. r0+width) (X: full-length vector; rows outside the block are not touched).  upper = 0: unit
+ * lower, 1: upper with diagonal. */
+extern "C" int updes_tri_diag_solve(UpdesLU *h, int slot, int upper, int64_t r0, int64_t c0, int64_t width, double *X,
+                                    void *stream) {
+  using namespace updes;
+  if (!h) return -1;
+  if (slot < 0 || slot >= UPDES_MAX_VIEWS || !h->view[slot].ptr) return -2;
+  if (r0 < 0 || width <= 0 || r0 + width > h->view[slot].rows) return -4;
+  if (c0 < 0 || (c0 & 1) || c0 + width > h->view[slot].ld) return -5;
+  if (!X) return -7;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = h->view[slot].rows;
+  double *Y = h->xbuf + (size_t)SOLVE_MAX_RHS * h->n;     // scratch for the solved block
+  const bool aligned = (r0 % SB) == 0 && ((width % SB) == 0 || r0 + width == n);
+  int rc;
+  prof_begin(PROF_SOLVE, 4.0 * (double)width * (double)width, st);
+  if (h->solve_variant == 2 && aligned)
+    rc = tri_sweep_rowblock(h, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, c0 - r0, (int)(r0 / SB),
+                            (int)((r0 + width + SB - 1) / SB), X, Y, n, 1, st, true);
+  else
+    rc = tri_block_sweep(h->num_sms, h->view[slot].ptr, h->view[slot].ld, n, upper != 0, r0, c0, width, X, Y, 1, st, true);
+  if (!rc) copy_block_kernel<<<(unsigned)((width + 255) / 256), 256, 0, st>>>(X, Y, n, r0, width, 1);
+  prof_end(st);
+  if (rc) return rc;
   UPDES_LAUNCH_CHECK();
   return 0;
 }

@@ -166,6 +166,22 @@ class CudaBackend:
         rc = self.lib.updes_tri_block_sweep(self.h, 0, 1 if upper else 0, r0, lc, w, x.data_ptr(), 1, _lib.stream_ptr())
         _lib.check(rc, "updes_tri_block_sweep")
 
+    def block_gemv(self, r0, w, c_lo, c_hi, xl, out):
+        """out[:w] = local[r0:r0+w, c_lo:c_hi] @ xl[c_lo:c_hi] (xl indexed by local column); zeros for an empty range."""
+        if c_hi <= c_lo:
+            out.zero_()
+            return
+        rc = self.lib.updes_block_gemv(self.h, 0, r0, w, c_lo, c_hi, xl.data_ptr(), out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "updes_block_gemv")
+
+    def diag_solve(self, upper, r0, lc, w, x):
+        """Triangular solve with the diagonal block of global block (rows r0.., local columns lc..) in place on x[r0:r0+w]."""
+        rc = self.lib.updes_tri_diag_solve(self.h, 0, 1 if upper else 0, r0, lc, w, x.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "updes_tri_diag_solve")
+
+    def zeros(self, k):
+        return self.torch.zeros(k, dtype=self.torch.float64, device=self.device)
+
     def vector(self, host_array):
         return self.torch.as_tensor(np.ascontiguousarray(host_array), dtype=self.torch.float64).to(self.device)
 
@@ -223,6 +239,7 @@ class DistributedLU:
         self.layout, self.rank, self.be, self.group = layout, rank, backend, group
         self.factored = False
         self.timeline = None          # set to [] to record per-panel events (bench.py's critical-path breakdown)
+        self.solve_variant = "left"   # "left": left-looking substitution (default); "right": first-generation column sweep
 
     def _src(self, r):
         """`layout` ranks are ranks of `group`; torch.distributed.broadcast wants the global rank."""
@@ -298,9 +315,60 @@ class DistributedLU:
         return out
 
     def solve(self, b_host):
-        """Solve K x = b (b: length-n host array, identical on all ranks) -> x as a device/host vector
-        replicated on every rank.  Column-sweep substitution: the owner of block j finishes x_j and
-        subtracts its block's contribution from the remaining rows, then broadcasts them."""
+        """Solve K x = b (b: length-n host array or device vector, identical on all ranks) -> x replicated on every rank.
+
+        Left-looking block substitution.  Row block j of L (or U) is spread over all ranks by columns, and each rank
+        only ever multiplies it with the solution entries of the blocks it owns and solved itself:
+            every rank:  p_r = L[rows j, my columns of blocks < j] . y[those]     (contiguous row segments, HBM rate,
+                                                                                   all ranks in parallel)
+            reduce p_r -> owner(j)   (width doubles);   owner:  y_j = L_jj^-1 (b_j - sum_r p_r)
+        so the chain per block is one small reduction + one diagonal-block solve, and the O(n^2) reads are shared by
+        all GPUs.  (The first version swept column blocks on the owner alone and broadcast the whole running
+        right-hand side after every block: serial in the matrix reads, 140 ms of a 2.4 s step at 8 GPUs.)"""
+        assert self.factored
+        if self.solve_variant == "right":
+            return self.solve_right_looking(b_host)
+        L, be, me, dist = self.layout, self.be, self.rank, self.dist
+        nb, n = L.nb, L.n
+        ncols = L.local_cols(me)
+        x = be.permute_rhs(b_host if hasattr(b_host, "data_ptr") else be.vector(b_host))
+        xl = be.zeros(max(ncols, 2))            # solved entries of MY blocks, indexed by local column
+        part = be.zeros(nb)
+        SUM = dist.ReduceOp.SUM
+        for j in range(L.nblocks):                                   # forward, unit lower
+            r0, w, o = j * nb, L.width(j), L.owner(j)
+            lc = L.local_offset(j) if o == me else None
+            hi = lc if o == me else L.local_offset_after(me, j)      # my columns of the blocks with global index < j
+            p = part[:w]
+            be.block_gemv(r0, w, 0, hi, xl, p)
+            dist.reduce(p, dst=self._src(o), op=SUM, group=self.group)
+            if o == me:
+                x[r0:r0 + w].sub_(p)
+                be.diag_solve(False, r0, lc, w, x)
+                xl[lc:lc + w].copy_(x[r0:r0 + w])
+        for j in range(L.nblocks - 1, -1, -1):                       # backward, upper
+            r0, w, o = j * nb, L.width(j), L.owner(j)
+            lc = L.local_offset(j) if o == me else None
+            lo = lc + w if o == me else L.local_offset_after(me, j)  # my columns of the blocks with global index > j
+            p = part[:w]
+            be.block_gemv(r0, w, lo, ncols, xl, p)
+            dist.reduce(p, dst=self._src(o), op=SUM, group=self.group)
+            if o == me:
+                x[r0:r0 + w].copy_(xl[lc:lc + w])
+                x[r0:r0 + w].sub_(p)
+                be.diag_solve(True, r0, lc, w, x)
+                xl[lc:lc + w].copy_(x[r0:r0 + w])
+        out = be.zeros(n)                                            # every rank contributes the blocks it solved
+        for j in L.local_blocks(me):
+            r0, w, lc = j * nb, L.width(j), L.local_offset(j)
+            out[r0:r0 + w].copy_(xl[lc:lc + w])
+        dist.all_reduce(out, op=SUM, group=self.group)
+        return out
+
+    def solve_right_looking(self, b_host):
+        """First-generation solve, kept for comparison (bench.py --dist-solve right) and as a second opinion in the
+        tests: column-sweep substitution; the owner of block j finishes x_j, subtracts its block's contribution from
+        the remaining rows and broadcasts them."""
         assert self.factored
         L, be, me, dist = self.layout, self.be, self.rank, self.dist
         nb, n = L.nb, L.n
