@@ -411,6 +411,10 @@ def run_gpu_arm(args):
     b = torch.as_tensor(q).cuda()
     K = torch.empty((n, asm.padded_ld(n)), dtype=torch.float64, device="cuda")
     lu = LUFactorization(K, n)
+    if args.trsm_base:
+        lu.set_trsm_base(args.trsm_base)
+    if args.gemm_variant >= 0:
+        lu.set_gemm_variant(args.gemm_variant)
     x = torch.empty_like(b)
 
     def step():
@@ -618,6 +622,7 @@ def run_gpu_arm_distributed(args, world, rank, local):
     layout = ColumnBlockCyclic(n, nb, world)
     be = CudaBackend(layout, rank, gemm_sms_reserved=args.reserve_sms)
     dlu = DistributedLU(layout, rank, be)
+    dlu.solve_variant = args.dist_solve
     b = be.vector(q)
     state = {}
 
@@ -784,6 +789,9 @@ def main():
     ap.add_argument("--no-library", action="store_true")
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--no-timeline", action="store_true")
+    ap.add_argument("--trsm-base", type=int, default=0, help="tuning hook (1 GPU): rows of the unit-lower solve's base kernel (32 / 128)")
+    ap.add_argument("--gemm-variant", type=int, default=-1, help="tuning hook (1 GPU): updes_lu_set_gemm_variant bits")
+    ap.add_argument("--dist-solve", default="left", choices=["left", "right"], help="multi-GPU substitution: left-looking (default) or the first-generation column sweep")
     args = ap.parse_args()
     try:
         if args.impl == "reference":

@@ -152,8 +152,10 @@ int updes_lu_bind(UpdesLU *handle, int slot, double *ptr, int64_t rows, int64_t 
 /* cap the persistent GEMM grid (0 = one CTA per SM) so NCCL kernels can run beside the update */
 int updes_lu_set_gemm_ctas(UpdesLU *handle, int ctas);
 /* trailing-update GEMM schedule, bit 0: 1 = ping-pong (two 128x64 CTAs per SM), 0 = one 128x128 CTA per SM;
- * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round); bits 2-5: distance (in pipeline stages) of
- * the producer's L2-only TMA prefetch, 0 = off; bits 6-7: operands it covers (1 = left tiles, 2 = right tiles) */
+ * bit 1: 32-deep pipeline stages (two 16-k sub-tiles per barrier round); bit 3: 1 = epilogue as a read-modify-write
+ * of C instead of the default fire-and-forget red.global.add.f64 (every C element belongs to exactly one thread of one
+ * launch, so both give the same bits); bit 2 (with bit 3): 1 = do not prefetch the C tile into L2 before that epilogue.
+ * Bits 2-3 are comparison hooks. */
 int updes_lu_set_gemm_variant(UpdesLU *handle, int variant);
 /* base panels: 2 (default) = implicit-pivoting kernels -- panels of <= 8 192 rows run in one thread-block cluster
  * whose CTAs push their candidates into each other's shared memory (one split cluster barrier per column), taller

@@ -18,7 +18,7 @@ def _matrix(n, seed=0, ld=None, dominant=False):
     return A, K.cuda()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 11, 15, 8])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 128, 64), (300, 200, 32), (1000, 96, 128), (77, 500, 48),
                                    (2048, 2048, 512), (129, 33, 16), (64, 32, 32), (4000, 64, 256), (5000, 3001, 96), (6000, 2500, 512)])
 def test_dgemm_sub(m, n, k, variant):
@@ -31,7 +31,7 @@ def test_dgemm_sub(m, n, k, variant):
     size = max(N, cols)
     _, K = _matrix(size, seed=m + n + k)
     lu = LUFactorization(K, size)
-    lu.set_gemm_variant(variant)          # 1 = ping-pong schedule (two 128x64 CTAs per SM) for wide updates
+    lu.set_gemm_variant(variant)          # bit 0: ping-pong (two 128x64 CTAs per SM); bit 1: 32-deep stages; bit 3: read-modify-write epilogue
     # A at (ra=k+32.., ca=0), B at (rb=0, cb=k+32), C at (k+32, k+32): an LU-like arrangement
     ra, ca, rb, cb = 32 + k, 0, 0, 32 + k
     rc, cc = 32 + k, 32 + k
@@ -234,22 +234,6 @@ def test_lu_singular_reports_info():
     assert lu.zero_pivot() == 41
 
 
-@pytest.mark.parametrize("variant", [1, 3, 3 | (4 << 2) | (3 << 6), 3 | (2 << 2) | (1 << 6), 1 | (8 << 2) | (2 << 6)])
-def test_dgemm_l2_prefetch_does_not_change_results(variant):
-    """The producer's L2-only TMA prefetch (distance / operand mask in the variant bits) is a pure hint."""
-    import torch
-    from updes_b200.linalg import LUFactorization
-    size, k = 3072, 512
-    _, K = _matrix(size, seed=11)
-    ref = K.clone()
-    ref[k:, k:size] -= ref[k:, :k] @ ref[:k, k:size]
-    lu = LUFactorization(K, size)
-    lu.set_gemm_variant(variant)
-    lu.gemm_sub(k, k, k, 0, 0, k, size - k, size - k, k)
-    torch.cuda.synchronize()
-    assert (K - ref).abs().max().item() <= 1e-12 * k * ref.abs().max().item()
-
-
 @pytest.mark.parametrize("n,r0,w,c_lo,c_hi", [(1000, 128, 128, 0, 128), (1000, 256, 100, 0, 991), (2051, 1024, 512, 512, 2051),
                                             (2051, 2048, 3, 64, 2048), (700, 0, 64, 0, 0), (5000, 1024, 1024, 0, 4096)])
 def test_block_gemv_partial_products(n, r0, w, c_lo, c_hi):
@@ -286,6 +270,8 @@ def test_tri_diag_solve_touches_only_its_block(n, r0, w, upper):
     lib = _lib.load()
     _lib.check(lib.updes_lu_bind(lu._handle, 0, K.data_ptr(), n, K.shape[1]), "bind")
     c0 = min((r0 // 2 + 64) & ~1, (K.shape[1] - w) & ~1)
+    idx = torch.arange(w, device="cuda")
+    K[r0 + idx, c0 + idx] += float(n)                  # a random triangular block would be exponentially ill-conditioned
     T = K[r0:r0 + w, c0:c0 + w]
     x = torch.randn(n, dtype=torch.float64, device="cuda")
     x0 = x.clone()
@@ -296,3 +282,34 @@ def test_tri_diag_solve_touches_only_its_block(n, r0, w, upper):
     keep = torch.ones(n, dtype=torch.bool, device="cuda"); keep[r0:r0 + w] = False
     assert torch.equal(x[keep], x0[keep])
     assert lu.check() == 0
+
+
+@pytest.mark.parametrize("n1,ncols,base", [(128, 200, 128), (128, 9600, 128), (96, 19100, 128), (128, 40000, 128), (64, 777, 128),
+                                          (512, 3000, 128), (512, 3000, 32), (1024, 1500, 128)])
+def test_trsm_unit_lower_blocks(n1, ncols, base):
+    """updes_lu_trsm: B <- L^-1 B for a unit-lower n1 x n1 block against ncols columns of the same buffer (the 128-row
+    substitution kernel in all three CTA sizes, the 32-row kernel, and the recursion above them) vs torch."""
+    import torch
+    from updes_b200 import _lib
+    from updes_b200.assembly import padded_ld
+    g = torch.Generator(device="cpu").manual_seed(n1 + ncols)
+    rows, ld = n1 + 40, padded_ld(n1 + 64 + ncols)
+    K = torch.randn((rows, ld), generator=g, dtype=torch.float64).cuda()
+    K[:, :n1 + 64] *= 0.05                                   # |multipliers| < 1 as after partial pivoting; keeps the solve tame
+    rl, cl, rb, cb = 8, 32, 8, n1 + 64                       # L at (8, 32), B at (8, n1 + 64): same rows, as inside the LU
+    ref = K.clone()
+    L = torch.tril(ref[rl:rl + n1, cl:cl + n1], -1) + torch.eye(n1, dtype=torch.float64, device="cuda")
+    ref[rb:rb + n1, cb:cb + ncols] = torch.linalg.solve_triangular(L, ref[rb:rb + n1, cb:cb + ncols], upper=False, unitriangular=True)
+    lib = _lib.load()
+    import ctypes
+    h = ctypes.c_void_p()
+    _lib.check(lib.updes_lu_create(ctypes.byref(h), rows, ld), "create")
+    _lib.check(lib.updes_lu_bind(h, 0, K.data_ptr(), rows, ld), "bind")
+    _lib.check(lib.updes_lu_set_trsm_base(h, base), "base")
+    _lib.check(lib.updes_lu_trsm(h, 0, rl, cl, n1, 0, rb, cb, ncols, _lib.stream_ptr()), "trsm")
+    torch.cuda.synchronize()
+    err = float((K - ref).abs().max() / ref[rb:rb + n1, cb:cb + ncols].abs().max())
+    assert err <= 1e-12, err
+    keep = torch.ones_like(K, dtype=torch.bool); keep[rb:rb + n1, cb:cb + ncols] = False
+    assert torch.equal(K[keep], ref[keep])
+    lib.updes_lu_destroy(h)

@@ -14,9 +14,9 @@ ld = padded_ld(n)
 K = torch.randn((n, ld), dtype=torch.float64, device="cuda")
 lu = LUFactorization(K, n)
 out = {}
-for variant in (1, 3):
+for variant in (3, 11):   # 3 = default (RED epilogue), 11 = read-modify-write epilogue with L2 prefetch
   lu.set_gemm_variant(variant)
-  for k in (128, 512, 1024, 2048):
+  for k in (128, 512, 1024, 2048, 8192):
     m = nn = n - k
     lu.gemm_sub(k, k, k, 0, 0, k, m, nn, k)          # warm-up
     torch.cuda.synchronize()

@@ -26,8 +26,8 @@ struct UpdesLU {
                            // 1: first-generation cluster + grid kernels; 0: first-generation grid kernel only
   int trsm_base_rows = 128; // largest block of the triangular solve handled by one substitution kernel (32: first generation)
   int gemm_kdeep = 1;      // 1 (default): 32-deep pipeline stages (two 16-k sub-tiles per barrier round) when k % 32 == 0
-  int gemm_pf_dist = 0;    // L2 prefetch distance of the GEMM's TMA producer, in pipeline stages (0 = off)
-  int gemm_pf_mask = 3;    // which operand tiles it prefetches (1: left, 2: right)
+  int gemm_epilogue = 1;   // 1 (default): fire-and-forget red.global.add.f64 (the SM never waits for C); 0: read-modify-write
+  int gemm_c_prefetch = 1; // read-modify-write epilogue only: pull each C tile into L2 one pipeline stage ahead
   int gemm_variant = 1;    // 1 (default): ping-pong, two 128x64 CTAs per SM; 0: one 128x128 CTA per SM
   MatView view[UPDES_MAX_VIEWS];
   void *workspace = nullptr;       // the one device allocation every pointer below points into

@@ -130,48 +130,82 @@ __global__ void __launch_bounds__(TRSM_THREADS) trsm_base_kernel(const double *L
 }
 
 // Base case for 32 < NB <= 128 (a multiple of 32): the same thread-per-column substitution, carried out in chunks of 32
-// rows.  The solved chunks of the CTA's 64 columns stay in shared memory next to L, so a chunk first takes the
-// contributions of all earlier chunks (independent FMAs, L broadcast from shared memory) and is then solved in
-// registers as above.  Replaces, per 128 rows, 4 launches of the 32-row kernel plus 3 tiny GEMM launches (k = 32, 64)
-// of the recursive solve: at n = 8192 those were 640 of the 1024 GEMM launches and 12 of 54 ms (29 ms with the base
-// launches), i.e. launch latency, not work.
+// rows.  A chunk first takes the contributions of all earlier (already final) rows, then is solved in registers as
+// above.  Replaces, per 128 rows, 4 launches of the 32-row kernel plus 3 tiny GEMM launches (k = 32, 64) of the
+// recursive solve, which were launch latency, not work.
+//   * L is staged TRANSPOSED in shared memory (Lt[j][i] = L[i][j]): for a fixed solved row j the 32 multipliers of a
+//     chunk are contiguous, so one broadcast LDS.128 feeds two FMAs (one LDS.64 per FMA made the first version
+//     LSU-issue bound);
+//   * the solved rows of a column are re-read from B itself (written by the same thread, coalesced across the warp,
+//     L1/L2 hits) instead of a 64 KB shared-memory copy: the CTA needs 130 KB, not 197 KB, and runs up to 256 threads
+//     (the first version ran 64 threads = 2 warps per SM: 440 ms of a 90k-node LU);
+//   * narrow right-hand sides use smaller CTAs so that the columns spread over all SMs.
 constexpr int TRSM_BIG = 128;
-constexpr int TRSM_BIG_SMEM = (TRSM_BIG * (TRSM_BIG + 1) + TRSM_BIG * TRSM_THREADS) * (int)sizeof(double);
-__global__ void __launch_bounds__(TRSM_THREADS) trsm_base_big_kernel(const double *Lm, long long ldl, long long rl, long long cl,
-                                                                     double *B, long long ldb, long long rb, long long cb,
-                                                                     long long ncols, int nb) {
-  extern __shared__ double trsm_sm[];
-  double *L = trsm_sm;                                   // [nb][TRSM_BIG + 1]
-  double *X = trsm_sm + TRSM_BIG * (TRSM_BIG + 1);       // [nb][TRSM_THREADS] solved rows of this CTA's columns
-  constexpr int LP = TRSM_BIG + 1;
-  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
-    const int i = t / nb, j = t - i * nb;
-    if (j < i) L[i * LP + j] = Lm[(rl + i) * ldl + cl + j];
+constexpr int TRSM_LPT = TRSM_BIG + 2;                   // even (16-byte pairs), and rows 4 banks apart for the staging writes
+constexpr int TRSM_BIG_SMEM = TRSM_BIG * TRSM_LPT * (int)sizeof(double);
+__global__ void __launch_bounds__(256) trsm_base_big_kernel(const double *__restrict__ Lm, long long ldl, long long rl, long long cl,
+                                                            double *B, long long ldb, long long rb, long long cb,
+                                                            long long ncols, int nb) {
+  extern __shared__ __align__(16) double trsm_sm[];
+  double *Lt = trsm_sm;                                  // Lt[j * TRSM_LPT + i] = L[i][j] for j < i < nb
+  // staging: 16 independent loads per thread in flight (with 64 threads a plain strided loop is 256 dependent-latency
+  // rounds, ~20 us: longer than the substitution itself)
+  {
+    const int total = nb * nb;
+    for (int t0 = threadIdx.x; t0 < total; t0 += 16 * blockDim.x) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        const int t = t0 + u * blockDim.x;
+        const int i = t / nb, j = t - i * nb;
+        v[u] = (t < total && j < i) ? Lm[(rl + i) * ldl + cl + j] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        const int t = t0 + u * blockDim.x;
+        const int i = t / nb, j = t - i * nb;
+        if (t < total && j < i) Lt[j * TRSM_LPT + i] = v[u];
+      }
+    }
   }
   __syncthreads();
   const long long c = cb + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cb + ncols) return;
-  double *Xc = X + threadIdx.x;
+  double *Bc = B + rb * ldb + c;
   for (int q0 = 0; q0 < nb; q0 += 32) {
     double x[32];
 #pragma unroll
-    for (int i = 0; i < 32; i++) x[i] = B[(rb + q0 + i) * ldb + c];
-    const double *Lq = L + q0 * LP;
-    for (int j = 0; j < q0; j++) {                       // earlier chunks
-      const double xj = Xc[j * TRSM_THREADS];
+    for (int i = 0; i < 32; i++) x[i] = Bc[(long long)(q0 + i) * ldb];
+    for (int j0 = 0; j0 < q0; j0 += 8) {                 // earlier, final rows: eight re-reads (L2 hits) in flight at a time
+      double xs[8];
 #pragma unroll
-      for (int i = 0; i < 32; i++) x[i] = fma(-Lq[i * LP + j], xj, x[i]);
+      for (int u = 0; u < 8; u++) xs[u] = -Bc[(long long)(j0 + u) * ldb];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double2 *lp = reinterpret_cast<const double2 *>(Lt + (j0 + u) * TRSM_LPT + q0);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const double2 l = lp[i];
+          x[2 * i] = fma(l.x, xs[u], x[2 * i]);
+          x[2 * i + 1] = fma(l.y, xs[u], x[2 * i + 1]);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 31; j++) {                       // this chunk, column-oriented
+    for (int j = 0; j < 31; j++) {                       // this chunk, column-oriented: the updates of x[j+1..] are independent
+      const double *lc = Lt + (q0 + j) * TRSM_LPT + q0;
+      const double xj = -x[j];
+      if ((j & 1) == 0) x[j + 1] = fma(lc[j + 1], xj, x[j + 1]);
 #pragma unroll
-      for (int i = j + 1; i < 32; i++) x[i] = fma(-Lq[i * LP + q0 + j], x[j], x[i]);
+      for (int i = (j + 2) & ~1; i < 32; i += 2) {
+        const double2 l = *reinterpret_cast<const double2 *>(lc + i);
+        x[i] = fma(l.x, xj, x[i]);
+        x[i + 1] = fma(l.y, xj, x[i + 1]);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-      if (q0 + i > 0) B[(rb + q0 + i) * ldb + c] = x[i];
-      Xc[(q0 + i) * TRSM_THREADS] = x[i];
-    }
+    for (int i = 0; i < 32; i++)
+      if (q0 + i > 0) Bc[(long long)(q0 + i) * ldb] = x[i];
   }
 }
 
@@ -186,8 +220,11 @@ static int trsm_base(UpdesLU *h, int vl, int64_t rl, int64_t cl, int nb, int vb,
       UPDES_CUDA_TRY(cudaFuncSetAttribute(trsm_base_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_BIG_SMEM));
       attr = true;
     }
+    // one CTA per SM (130 KB of shared memory): the smallest CTA that still covers the columns in one wave
+    const int threads = ncols <= 64LL * h->num_sms ? 64 : (ncols <= 128LL * h->num_sms ? 128 : 256);
+    const unsigned gridb = (unsigned)((ncols + threads - 1) / threads);
     prof_begin(PROF_TRSM, (double)nb * nb * (double)ncols, st);
-    trsm_base_big_kernel<<<grid, TRSM_THREADS, TRSM_BIG_SMEM, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols, nb);
+    trsm_base_big_kernel<<<gridb, threads, TRSM_BIG_SMEM, st>>>(VL.ptr, VL.ld, rl, cl, VB.ptr, VB.ld, rb, cb, ncols, nb);
     prof_end(st);
     UPDES_LAUNCH_CHECK();
     return 0;
