@@ -333,9 +333,13 @@ def small_configs(u, torch):
     import configs
     from updes_b200 import _lib
 
-    def timed(fn, reps):
+    def timed(fn, reps, before=None):
+        """median wall-clock ms of fn(); `before` (dropping the factor cache: cudaFree of cached blocks, whose cost
+        depends on what else the process has allocated) runs outside the timed region"""
         ts = []
         for _ in range(reps):
+            if before:
+                before()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             fn()
@@ -346,24 +350,23 @@ def small_configs(u, torch):
     out = {}
     cloud, solve = configs.config1(u)
 
-    def c1():
-        u.clear_cache()
-        return solve()
-    c1()
+    u.clear_cache()
+    solve()
     l0 = _lib.launch_count()
-    out["config1_laplace_30x20"] = {"N": cloud.N, "e2e_ms": timed(c1, 5), "launches": (_lib.launch_count() - l0) // 5,
-                                    "what": "lowering + assembly + LU + solve + refinement, factor cache cleared every call"}
+    out["config1_laplace_30x20"] = {"N": cloud.N, "e2e_ms": timed(solve, 5, before=u.clear_cache), "launches": (_lib.launch_count() - l0) // 5,
+                                    "what": "lowering + assembly + LU + solve + refinement; the factor cache is emptied before every call"}
+    out["config1_laplace_30x20"]["e2e_ms_factor_cached"] = timed(solve, 5)
     cloud, u0, step, _ = configs.config2(u)
     state = {"u": u0}
 
     def c2_first():
-        u.clear_cache()
         state["u"] = step(u0).vals
 
     def c2_step():
         state["u"] = step(state["u"]).vals
+    u.clear_cache()
     c2_first()
-    out["config2_advdiff_periodic_35x35"] = {"N": cloud.N, "first_step_ms": timed(c2_first, 3), "per_step_ms_factor_cached": timed(c2_step, 10),
+    out["config2_advdiff_periodic_35x35"] = {"N": cloud.N, "first_step_ms": timed(c2_first, 3, before=u.clear_cache), "per_step_ms_factor_cached": timed(c2_step, 10),
                                              "what": "first step factors K and A; later steps: coefficients of u (A solve), rhs, two sweeps"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -372,10 +375,10 @@ def small_configs(u, torch):
         cp, _ = cloud_from_golden("mesh_msh_cloud_phi.npz")
 
         def c3():
-            u.clear_cache()
             configs.config3_projection_loop(u, cv, cp, nb_iter=2)
+        u.clear_cache()
         c3()
-        out["config3_navier_stokes_projection_1385"] = {"N": cv.N, "ms_per_iteration": timed(c3, 3) / 2.0,
+        out["config3_navier_stokes_projection_1385"] = {"N": cv.N, "ms_per_iteration": timed(c3, 3, before=u.clear_cache) / 2.0,
                                                         "what": "u, v (re-assembled + re-factored: the matrix depends on the previous velocity) and phi "
                                                                 "(factor cached) solves per iteration, mesh.msh clouds, 2 iterations averaged"}
     except Exception as e:  # the mesh fixture lives under tests/golden
@@ -476,14 +479,22 @@ def run_gpu_arm(args):
     op, rhs, bcs = api_problem(u, cloud)
     e2e_times = []
     sol = None
+    from updes_b200 import operators as ops
+    e2e_phases = None
     for i in range(args.e2e_steps + 1):
         sol = None
         u.clear_cache()
+        last = i == args.e2e_steps
+        ops.TRACE = [] if last else None          # phase marks (a device synchronize each) on the last call only
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        ops._trace_t[0] = t0
         sol = u.pde_solver_jit(op, rhs, cloud, bcs, u.polyharmonic, 1)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if last:
+            e2e_phases = [[k.strip(), round(v * 1e3, 3)] for k, v in ops.TRACE]
+            ops.TRACE = None
         if i > 0 or args.e2e_steps == 0:
             e2e_times.append(dt)
     u.clear_cache()
@@ -538,7 +549,7 @@ def run_gpu_arm(args):
             "seconds_per_step": ms_step * 1e-3,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "seconds_per_step": e2e_s, "api": "updes_b200.pde_solver_jit (numpy in, numpy out; row equilibration + 1 refinement step)",
-                    "max_err_vs_analytic": e2e_err},
+                    "max_err_vs_analytic": e2e_err, "phases_ms_last_call": e2e_phases},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "breakdown": breakdown,
             "cpu_baseline": cpu, "library_baseline": library, "small_configs": small,
             "correctness": {"backward_error": berr, "max_err_vs_analytic": max_err, "zero_pivot": status}}

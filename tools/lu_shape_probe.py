@@ -75,4 +75,4 @@ def probe(n, base=128):
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [8192]
-    print(json.dumps([probe(n, b) for n in sizes for b in (128, 32)]))
+    print(json.dumps([probe(n, b) for n in sizes for b in (128, 64, 32)]))

@@ -500,6 +500,22 @@ class SteadySol:
 
 FactorizationError = RuntimeError     # internal device-side failures (never a numerical status) raise RuntimeError
 
+# Optional phase timing of pde_solver (tools/e2e_phases.py): set to a list to collect (phase, seconds since the previous
+# mark) with a device synchronize at every mark; None (default) costs one comparison per mark.
+TRACE = None
+_trace_t = [0.0]
+
+
+def _mark(phase):
+    if TRACE is None:
+        return
+    import time
+    import torch
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    TRACE.append((phase, now - _trace_t[0]))
+    _trace_t[0] = now
+
 
 class _System:
     """An assembled + factored collocation system resident on the GPU."""
@@ -507,10 +523,14 @@ class _System:
     def __init__(self, cloud, kind, param, M, table, equilibrate=True):
         self.kind, self.param, self.M = kind, param, M
         self.cloud = cloud                   # the cache key uses id(cloud): keep it alive while cached
+        _mark("  digest + row descriptors (host)")
         self.rows = _asm.DeviceRows(cloud, table)
+        _mark("  row descriptors -> device")
         self.K = _asm.assemble_system(self.rows, kind, param, M)
+        _mark("  allocate K + assembly")
         self.n = cloud.N + M
         self.lu = LUFactorization(self.K, self.n).factor(equilibrate=equilibrate)
+        _mark("  equilibration + LU")
 
     def check(self):
         """Raise on internal failures; return the LAPACK-style zero-pivot status (0 = none)."""
@@ -570,11 +590,12 @@ def _dist_world(distributed=None):
 
 
 def default_block_width(n, world):
-    """Column-block width of the multi-GPU layout: 2048 for large systems (the update GEMM reaches
-    33 TFLOP/s at k = 2048 vs 29 at k = 512), smaller when the matrix would otherwise have fewer than
-    ~8 blocks per rank."""
+    """Column-block width of the multi-GPU layout: 2048 for large systems, halved until every rank owns at least
+    ~12 blocks.  With the fire-and-forget GEMM epilogue the update loses little at a smaller inner dimension
+    (35.5 / 35.1 / 34.4 TFLOP/s at k = 2048 / 1024 / 512), while few blocks per rank cost balance: at 4 GPUs and
+    n = 90 003, nb = 2048 (11 blocks per rank) left the last rank 250 ms (6 %) more trailing update than the first."""
     nb = 2048
-    while nb > 64 and n // (nb * world) < 8:
+    while nb > 64 and n // (nb * world) < 12:
         nb //= 2
     return nb
 
@@ -748,11 +769,13 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     the time loops of demos/Advection -- only pay for the right-hand side and two triangular sweeps.
     Keyword-only extras: ``refine`` (iterative-refinement steps, default 1), ``distributed`` (None = follow
     ``enable_distributed()``; True/False forces the sharded / single-GPU path for this call)."""
+    _mark("enter")
     kind, param = identify_rbf(rbf)
     robin_coeffs, boundary_conditions = duplicate_robin_coeffs(dict(boundary_conditions), cloud)
     boundary_conditions = zerofy_periodic_cond(boundary_conditions, cloud)
     M = compute_nb_monomials(max_degree, cloud.dim)
     coef_phi, coef_pol = lower_diff_operator(diff_operator, cloud, rbf, diff_args)
+    _mark("bc preparation + operator lowering")
     betas = np.array([robin_coeffs[k] for k in sorted(robin_coeffs)], dtype=np.float64) if robin_coeffs else None
 
     world, rank, group = _dist_world(distributed)
@@ -764,9 +787,12 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
                                 _DistSystem.predict_nbytes(n, world))
     else:
         system = _cached_system(key, lambda: _System(cloud, kind, param, M, table_fn()), _System.predict_nbytes(n))
+    _mark("digest + row descriptors + assembly + equilibration + LU (or cache hit)")
     q = assemble_q(rhs_operator, boundary_conditions, cloud, rbf, M, rhs_args)
+    _mark("right-hand side")
     coeffs_dev = system.solve(np.concatenate([q, np.zeros(M)]), refine=refine)
     zero_pivot = system.check()              # raises FactorizationError on internal failures
+    _mark("solve + refinement + status")
     if zero_pivot:
         warnings.warn("collocation matrix is exactly singular (zero pivot at column %d)" % zero_pivot)
     # vals = [Phi P] c with the reference's zero-diagonal Phi (assembly.py:31-32, :404-410)
@@ -775,6 +801,7 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     jphi, jpol = _asm.eval_jets(kind, param, system.rows.centres, coeffs_dev.view(1, -1), system.rows.centres, own)
     vals = (jphi[0, :, 0] + jpol[0, :, 0]).cpu().numpy()
     coeffs = coeffs_dev.cpu().numpy()
+    _mark("vals = [Phi P] c + download")
     # the lazy ``mat`` holds host descriptors only (never `system`): solutions must not pin the factors in HBM
     table = system.rows.table
     if world > 1:
