@@ -313,3 +313,43 @@ def test_trsm_unit_lower_blocks(n1, ncols, base):
     keep = torch.ones_like(K, dtype=torch.bool); keep[rb:rb + n1, cb:cb + ncols] = False
     assert torch.equal(K[keep], ref[keep])
     lib.updes_lu_destroy(h)
+
+
+@pytest.mark.parametrize("rows,ncols,k0,npiv", [(400, 300, 0, 32), (3000, 1000, 64, 512), (5000, 777, 100, 70), (2048, 4096, 0, 2048), (900, 64, 10, 1)])
+def test_apply_swaps_many_pivots_in_one_launch(rows, ncols, k0, npiv):
+    """updes_lu_apply_swaps: interchanges (k0+t <-> ipiv[k0+t]), t = 0..npiv-1, in order, on a column range; every
+    batch of 32 inside one launch.  Pivot lists with repeats, self-swaps and targets inside later batches."""
+    import ctypes
+    import torch
+    from updes_b200 import _lib
+    from updes_b200.assembly import padded_ld
+    g = torch.Generator(device="cpu").manual_seed(rows + npiv)
+    ld = padded_ld(ncols + 40)
+    K = torch.randn((rows, ld), generator=g, dtype=torch.float64).cuda()
+    piv = torch.zeros(rows, dtype=torch.int32)
+    for t in range(npiv):
+        r = int(torch.randint(0, 10, (1,), generator=g))
+        if r < 2:
+            p = k0 + t                                           # self
+        elif r < 5:
+            p = min(rows - 1, k0 + t + int(torch.randint(0, 40, (1,), generator=g)))   # a nearby row (often a later diagonal row)
+        else:
+            p = int(torch.randint(k0 + t, rows, (1,), generator=g))
+        piv[k0 + t] = p
+    ref = K.clone()
+    c_lo, c_hi = 16, 16 + ncols
+    for t in range(npiv):
+        p = int(piv[k0 + t])
+        if p != k0 + t:
+            tmp = ref[k0 + t, c_lo:c_hi].clone()
+            ref[k0 + t, c_lo:c_hi] = ref[p, c_lo:c_hi]
+            ref[p, c_lo:c_hi] = tmp
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    _lib.check(lib.updes_lu_create(ctypes.byref(h), rows, ld), "create")
+    _lib.check(lib.updes_lu_bind(h, 0, K.data_ptr(), rows, ld), "bind")
+    pd = piv.cuda()
+    _lib.check(lib.updes_lu_apply_swaps(h, 0, c_lo, c_hi, k0, npiv, pd.data_ptr(), _lib.stream_ptr()), "swaps")
+    torch.cuda.synchronize()
+    assert torch.equal(K, ref)
+    lib.updes_lu_destroy(h)

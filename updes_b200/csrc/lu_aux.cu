@@ -16,12 +16,23 @@ constexpr int SWAP_MAX_PIV = 32;
 
 // Columns: the range [c0, c0+ncols) with the hole [hole0, hole0+holew) left out (the panel's own columns, which the
 // panel kernel already wrote in final row order): one launch covers the columns left AND right of a base panel.
+// The kernel walks through ALL npiv_total interchanges in batches of 32: a thread owns one column for the whole launch,
+// so consecutive batches need no synchronisation beyond the two barriers around the shared slot tables (the
+// multi-GPU path applies 512 - 2048 interchanges per panel to every local column: one launch instead of 16 - 64).
 __global__ void __launch_bounds__(SWAP_THREADS) swap_rows_kernel(double *K, long long ld, long long c0, long long ncols,
                                                                 long long hole0, long long holew,
-                                                                long long k0, int npiv, const int32_t *ipiv) {
+                                                                long long k_first, int npiv_total, const int32_t *ipiv) {
   // slots 0..31: the diagonal rows k0+s; slots 32..63: pivot rows outside [k0, k0+npiv), in order of first use
   __shared__ int s_row[64];      // row held by a slot (-1: unused)
   __shared__ int s_src[64];      // slot whose ORIGINAL content ends up in this slot
+  const long long tcol = (long long)blockIdx.x * SWAP_THREADS + threadIdx.x;
+  long long c = c0 + tcol;
+  if (c >= hole0) c += holew;
+  const bool active = tcol < ncols - holew;
+  for (int b0 = 0; b0 < npiv_total; b0 += SWAP_MAX_PIV) {
+  const long long k0 = k_first + b0;
+  const int npiv = min(SWAP_MAX_PIV, npiv_total - b0);
+  if (b0 > 0) __syncthreads();   // every thread has read the previous batch's tables
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     // all pivots in ONE load (a load per loop step is 32 dependent global round trips: ~10 us of a ~15 us kernel)
@@ -56,19 +67,18 @@ __global__ void __launch_bounds__(SWAP_THREADS) swap_rows_kernel(double *K, long
     s_src[32 + lane] = row_hi >= 0 ? src_hi : 32 + lane;
   }
   __syncthreads();
-  const long long t = (long long)blockIdx.x * SWAP_THREADS + threadIdx.x;
-  if (t >= ncols - holew) return;
-  long long c = c0 + t;
-  if (c >= hole0) c += holew;
-  double v[64];
+  if (active) {
+    double v[64];
 #pragma unroll
-  for (int s = 0; s < 64; s++) {
-    const int src = s_src[s];
-    if (src != s) v[s] = K[(long long)s_row[src] * ld + c];
+    for (int s = 0; s < 64; s++) {
+      const int src = s_src[s];
+      if (src != s) v[s] = K[(long long)s_row[src] * ld + c];
+    }
+#pragma unroll
+    for (int s = 0; s < 64; s++) {
+      if (s_src[s] != s) K[(long long)s_row[s] * ld + c] = v[s];
+    }
   }
-#pragma unroll
-  for (int s = 0; s < 64; s++) {
-    if (s_src[s] != s) K[(long long)s_row[s] * ld + c] = v[s];
   }
 }
 
@@ -82,14 +92,12 @@ int swap_rows_hole(UpdesLU *h, int v, int64_t c0, int64_t ncols, int64_t hole0, 
   double *K = h->view[v].ptr;
   const long long ld = h->view[v].ld;
   if (!K) return -2;
-  for (int64_t t0 = 0; t0 < npiv; t0 += SWAP_MAX_PIV) {
-    const int np = (int)((npiv - t0) < SWAP_MAX_PIV ? (npiv - t0) : SWAP_MAX_PIV);
-    prof_begin(PROF_SWAP, 32.0 * (double)work * np, st);
-    swap_rows_kernel<<<(unsigned)((work + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
-        K, ld, c0, ncols, hole0, holew, k0 + t0, np, ipiv);
-    prof_end(st);
-    UPDES_LAUNCH_CHECK();
-  }
+  if (npiv > 0x7fffffff) return -6;
+  prof_begin(PROF_SWAP, 32.0 * (double)work * (double)npiv, st);
+  swap_rows_kernel<<<(unsigned)((work + SWAP_THREADS - 1) / SWAP_THREADS), SWAP_THREADS, 0, st>>>(
+      K, ld, c0, ncols, hole0, holew, k0, (int)npiv, ipiv);
+  prof_end(st);
+  UPDES_LAUNCH_CHECK();
   return 0;
 }
 
