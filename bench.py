@@ -406,6 +406,10 @@ def run_gpu_arm(args):
         # from the update GEMM they overlap with (the GEMM's dynamic tile scheduler absorbs the rest)
         os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.grid:
+            P, Q = (int(v) for v in args.grid.lower().split("x"))
+            if P > 1:
+                return run_gpu_arm_grid2d(args, world, rank, local, P, Q)
         return run_gpu_arm_distributed(args, world, rank, local)
 
     nx = args.nx if args.nx else HEADLINE_NX
@@ -745,6 +749,86 @@ def run_gpu_arm_distributed(args, world, rank, local):
     dist.destroy_process_group()
 
 
+def run_gpu_arm_grid2d(args, world, rank, local, P, Q):
+    """Comparison hook (`--grid PxQ`, P > 1): the same strong-scaling step on the 2-D block-cyclic layout of
+    updes_b200/grid2d.py.  NOT the default and not part of the driver's series: the measured layout is 1 x Q."""
+    import torch
+    import torch.distributed as dist
+    import updes_b200 as u
+    from updes_b200 import _lib, assembly as asm
+    from updes_b200.grid2d import BlockCyclic2D, CudaKernels2D, DistributedLU2D
+    from updes_b200.operators import default_block_width
+    assert P * Q == world, "--grid PxQ must match the number of ranks"
+    nx = args.nx if args.nx else HEADLINE_NX
+    cloud, M, n, table, rows, q, exact = headline_problem(u, asm, nx)
+    nb = args.nb or default_block_width(n, max(P, Q))
+    layout = BlockCyclic2D(n, nb, P, Q)
+    dlu = DistributedLU2D(layout, rank, CudaKernels2D())
+    b = torch.as_tensor(q).cuda()
+    state = {}
+
+    def step():
+        dlu.assemble(rows, "polyharmonic", 1.0, M)
+        dlu.factor()
+        state["x"] = dlu.solve(b)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.profile_enable(True)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    prof = {k: _lib.profile_read(k) for k in ("gemm", "panel", "swap", "trsm", "assemble", "solve")}
+    _lib.profile_enable(False)
+    x = state["x"]
+    r = b - asm.apply_rows(rows, "polyharmonic", 1.0, M, x.view(1, -1))[0]
+    own = torch.arange(cloud.N, dtype=torch.int32, device="cuda")
+    jphi, jpol = asm.eval_jets("polyharmonic", 1.0, rows.centres, x.view(1, -1), rows.centres, own)
+    max_err = float(np.max(np.abs((jphi[0, :, 0] + jpol[0, :, 0]).cpu().numpy() - exact)))
+    dlu.assemble(rows, "polyharmonic", 1.0, M)
+    rs = dlu.local[:, :dlu.cvalid].abs().sum(dim=1)                     # ||K||_inf: row sums add along the process row
+    dist.all_reduce(rs, group=dlu.row_groups[dlu.p])
+    kn = rs.max().reshape(1)
+    dist.all_reduce(kn, op=dist.ReduceOp.MAX)
+    berr = float(r.abs().max().item() / (kn.item() * x.abs().max().item() + b.abs().max().item()))
+    status = dlu.zero_pivot()
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        g_ms, g_flops, g_cnt = prof["gemm"]
+        gemm_tf = g_flops / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else 0.0
+        value = lu_flops(n) / (ms_step * 1e-3) * 1e-12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(nx), "n": n, "matrix_bytes": 8 * n * n, "lu_flops": lu_flops(n),
+                           "parallelism": "%dx%d 2-D block-cyclic, nb=%d, centralised panel factorisation, no look-ahead (comparison hook)" % (P, Q, nb),
+                           "l2": "local matrix (%.1f GB) is far larger than L2; no flush needed" % (8 * n * n / world / 1e9)},
+                "seconds_per_step": ms_step * 1e-3, "e2e": None, "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "dgemm_sub_kernel (DMMA m8n8k4 + TMA) on rank 0", "bound": "tensor", "achieved": gemm_tf, "peak": peak,
+                             "unit": "TFLOP/s", "frac": gemm_tf / peak, "traffic": None,
+                             "share_of_step": g_ms / (ms_step * args.steps), "peak_source": peak_src},
+                "breakdown": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] // max(args.steps, 1)} for k, v in prof.items()},
+                "per_gpu_tflops": value / world, "cpu_baseline": None,
+                "correctness": {"backward_error": berr, "max_err_vs_analytic": max_err, "zero_pivot": status}}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def run_config5(args, world, rank, torch, dist, u, asm, _lib):
     from updes_b200.distributed import ColumnBlockCyclic, CudaBackend, DistributedLU
     from updes_b200.operators import default_block_width
@@ -789,6 +873,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=0, help="SquareCloud side (default 300: the 90k-node headline config, at every GPU count)")
     ap.add_argument("--nb", type=int, default=0, help="column-block width of the multi-GPU layout (default: auto)")
+    ap.add_argument("--grid", default="", help="comparison hook (multi-GPU): PxQ with P > 1 runs the 2-D block-cyclic layout of updes_b200/grid2d.py instead of 1xQ")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left free by the update GEMM for NCCL (multi-GPU)")
     ap.add_argument("--cpu-nx", type=int, default=70, help="side of the bounded CPU sample of the reference arm's steps")
     ap.add_argument("--cpu-sizes", default="30x20,50x50,100x100", help="clouds of the CPU size sweep (BASELINE.md 4.3: N = 600, 2 500, 10 000)")

@@ -392,3 +392,49 @@ def test_distributed_path_is_opt_in():
         u.enable_distributed()                           # no process group
     with pytest.raises(RuntimeError):
         ops._dist_world(distributed=True)
+
+
+def test_distributed_layout_selection(monkeypatch):
+    """enable_distributed(grid=(P, Q)): P > 1 builds the 2-D system, everything else the measured 1 x Q system;
+    the builder passes the row table through and the predicted footprints are sane (no GPU: stub systems)."""
+    import torch.distributed as dist
+    from updes_b200 import operators as ops
+    made = []
+
+    class Stub1:
+        def __init__(self, cloud, kind, param, M, table, world, rank, group=None):
+            made.append(("1xQ", table, world, rank, group))
+        predict_nbytes = staticmethod(ops._DistSystem.predict_nbytes)
+
+    class Stub2:
+        def __init__(self, cloud, kind, param, M, table, grid, rank, group=None):
+            made.append(("PxQ", table, grid, rank, group))
+        predict_nbytes = staticmethod(ops._DistSystem2D.predict_nbytes)
+
+    monkeypatch.setattr(ops, "_DistSystem", Stub1)
+    monkeypatch.setattr(ops, "_DistSystem2D", Stub2)
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 4)
+    monkeypatch.setattr(dist, "get_rank", lambda group=None: 3)
+    cloud = u.SquareCloud(Nx=8, Ny=8, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+    try:
+        ops.enable_distributed()
+        assert ops._dist_world() == (4, 3, None) and ops._DIST["grid"] is None
+        build, need = ops._make_dist_system(cloud, "polyharmonic", 1.0, 3, lambda: "TABLE", 4, 3, None)
+        build()
+        assert made[-1] == ("1xQ", "TABLE", 4, 3, None) and need == ops._DistSystem.predict_nbytes(cloud.N + 3, 4)
+        ops.enable_distributed(grid=(1, 4))                     # 1 x Q spelled as a grid is still the default path
+        assert ops._DIST["grid"] is None
+        ops.enable_distributed(grid=(2, 2))
+        build, need = ops._make_dist_system(cloud, "polyharmonic", 1.0, 3, lambda: "TABLE", 4, 3, None)
+        build()
+        assert made[-1] == ("PxQ", "TABLE", (2, 2), 3, None) and need == ops._DistSystem2D.predict_nbytes(cloud.N + 3, (2, 2))
+        with pytest.raises(ValueError):
+            ops.enable_distributed(grid=(3, 2))                 # 6 != 4 ranks
+        # footprints at the sizes the layouts are for: 250k nodes on 8 GPUs is ~62.5 GB of matrix per rank either way
+        n = 250003
+        assert 62e9 < ops._DistSystem.predict_nbytes(n, 8) < 75e9
+        assert 62e9 < ops._DistSystem2D.predict_nbytes(n, (2, 4)) < 85e9   # + gathered panel, panel rows, U12 and row-exchange staging
+    finally:
+        ops.disable_distributed()
+    assert ops._DIST == {"enabled": False, "group": None, "grid": None}

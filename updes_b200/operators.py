@@ -556,24 +556,32 @@ class _System:
 
 
 # ---- multi-GPU opt-in ---------------------------------------------------------------------------------
-_DIST = {"enabled": False, "group": None}
+_DIST = {"enabled": False, "group": None, "grid": None}
 
 
-def enable_distributed(group=None):
+def enable_distributed(group=None, grid=None):
     """Shard every subsequent ``pde_solver*`` call over the ranks of ``group`` (default: the default
     ``torch.distributed`` process group, which must already be initialised with the NCCL backend, one
     process per GPU).  EVERY rank of the group must then call the solver with identical arguments.
     Opt-in on purpose: an initialised process group alone (e.g. inside an unrelated data-parallel job)
-    does not change how ``pde_solver`` runs."""
+    does not change how ``pde_solver`` runs.
+
+    ``grid=(P, Q)`` with P > 1 selects the 2-D block-cyclic layout (updes_b200/grid2d.py; P * Q must equal the
+    group size); the default is the measured 1 x Q column-block-cyclic layout (updes_b200/distributed.py)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("enable_distributed() needs an initialised torch.distributed process group (backend nccl)")
-    _DIST["enabled"], _DIST["group"] = True, group
+    if grid is not None:
+        P, Q = int(grid[0]), int(grid[1])
+        if P < 1 or Q < 1 or P * Q != dist.get_world_size(group):
+            raise ValueError("grid=(%d, %d) does not match the %d ranks of the process group" % (P, Q, dist.get_world_size(group)))
+        grid = (P, Q) if P > 1 else None           # 1 x Q is the default path
+    _DIST["enabled"], _DIST["group"], _DIST["grid"] = True, group, grid
     clear_cache()
 
 
 def disable_distributed():
-    _DIST["enabled"], _DIST["group"] = False, None
+    _DIST["enabled"], _DIST["group"], _DIST["grid"] = False, None, None
     clear_cache()
 
 
@@ -647,6 +655,59 @@ class _DistSystem:
         return n * _asm.padded_ld(cols) * 8 + 2 * (n * nb + nb) * 8
 
 
+class _DistSystem2D:
+    """The same system on a P x Q block-cyclic process grid (updes_b200/grid2d.py); selected by
+    ``enable_distributed(grid=(P, Q))`` with P > 1.  Same interface as ``_DistSystem``."""
+
+    def __init__(self, cloud, kind, param, M, table, grid, rank, group=None):
+        from .grid2d import BlockCyclic2D, CudaKernels2D, DistributedLU2D
+        self.kind, self.param, self.M = kind, param, M
+        self.cloud = cloud
+        self.group = group
+        self.rows = _asm.DeviceRows(cloud, table)
+        self.n = cloud.N + M
+        P, Q = grid
+        self.layout = BlockCyclic2D(self.n, default_block_width(self.n, max(P, Q)), P, Q)
+        self.dlu = DistributedLU2D(self.layout, rank, CudaKernels2D(), group=group)
+        self.dlu.assemble(self.rows, kind, param, M)
+        self.dlu.equilibrate().factor()
+        self.K = self.dlu.local
+
+    def check(self):
+        status = self.dlu.zero_pivot()
+        if status < 0:
+            raise FactorizationError("the panel kernel's grid barrier timed out on some rank (info = %d)" % status)
+        self.dlu.K.check_sweeps()
+        return status
+
+    def solve(self, rhs, refine=1):
+        torch = self.rows.torch
+        b = torch.as_tensor(rhs, dtype=torch.float64).to(self.dlu.device)
+        c = self.dlu.solve(b)
+        for _ in range(refine):
+            r = b - _asm.apply_rows(self.rows, self.kind, self.param, self.M, c.view(1, -1))[0]
+            c = c + self.dlu.solve(r)
+        return c
+
+    def nbytes(self):
+        return self.dlu.nbytes()
+
+    @staticmethod
+    def predict_nbytes(n, grid):
+        P, Q = grid
+        nb = default_block_width(n, max(P, Q))
+        mloc, ld = -(-n // (nb * P)) * nb + nb, -(-n // (nb * Q)) * nb + nb
+        return 8 * (mloc * ld + (n + nb) * nb + 2 * (mloc * nb + nb) + 3 * nb * ld)
+
+
+def _make_dist_system(cloud, kind, param, M, table, world, rank, group):
+    """(builder, predicted bytes) of the sharded system in the layout enable_distributed() selected."""
+    grid = _DIST["grid"]
+    if grid is not None and grid[0] * grid[1] == world:
+        return (lambda: _DistSystem2D(cloud, kind, param, M, table(), grid, rank, group)), _DistSystem2D.predict_nbytes(cloud.N + M, grid)
+    return (lambda: _DistSystem(cloud, kind, param, M, table(), world, rank, group)), _DistSystem.predict_nbytes(cloud.N + M, world)
+
+
 # ---- cache of factored systems -----------------------------------------------------------------------------
 _CACHE: "OrderedDict[tuple, object]" = OrderedDict()
 _CACHE_FRACTION = 0.88        # of the device's total memory, shared by all cached systems
@@ -705,11 +766,11 @@ def _interp_system(cloud, kind, param, M, distributed=None):
     """Factorisation of A = [[Phi P], [P^T 0]] (assembly.py:62-90), cached per (cloud, rbf, M).  On the
     multi-GPU path A is sharded like K (an (N+M)^2 matrix per rank would not fit at the sizes that path is for)."""
     world, rank, group = _dist_world(distributed)
-    key = ("A", id(cloud), kind, param, M, world)
+    key = ("A", id(cloud), kind, param, M, world, _DIST["grid"] if world > 1 else None)
     n = cloud.N + M
     if world > 1:
-        return _cached_system(key, lambda: _DistSystem(cloud, kind, param, M, _asm.build_interpolation_rows(cloud), world, rank, group),
-                              _DistSystem.predict_nbytes(n, world))
+        build, need = _make_dist_system(cloud, kind, param, M, lambda: _asm.build_interpolation_rows(cloud), world, rank, group)
+        return _cached_system(key, build, need)
     return _cached_system(key, lambda: _System(cloud, kind, param, M, _asm.build_interpolation_rows(cloud)),
                           _System.predict_nbytes(n))
 
@@ -779,12 +840,12 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     betas = np.array([robin_coeffs[k] for k in sorted(robin_coeffs)], dtype=np.float64) if robin_coeffs else None
 
     world, rank, group = _dist_world(distributed)
-    key = ("K", id(cloud), kind, param, M, _digest(coef_phi, coef_pol, betas), world)
+    key = ("K", id(cloud), kind, param, M, _digest(coef_phi, coef_pol, betas), world, _DIST["grid"] if world > 1 else None)
     n = cloud.N + M
     table_fn = lambda: _asm.build_operator_rows(cloud, coef_phi, coef_pol, betas)
     if world > 1:
-        system = _cached_system(key, lambda: _DistSystem(cloud, kind, param, M, table_fn(), world, rank, group),
-                                _DistSystem.predict_nbytes(n, world))
+        build, need = _make_dist_system(cloud, kind, param, M, table_fn, world, rank, group)
+        system = _cached_system(key, build, need)
     else:
         system = _cached_system(key, lambda: _System(cloud, kind, param, M, table_fn()), _System.predict_nbytes(n))
     _mark("digest + row descriptors + assembly + equilibration + LU (or cache hit)")
