@@ -11,10 +11,17 @@ Contents (reference file:line in each docstring):
   * assemble_q, reference_solve   -- the reference *formulation*: inv(A), B = D inv(A)[:, :N],
     QR solve of B u = q, coefficients inv(A)[u; 0]   (assembly.py:366-410, operators.py:602-616)
 
-PARITY PIN STATUS: "parity unpinned" at the per-entry level -- the reference needs jax/jaxlib/
-lineax, none of which exist in this image, and its tests hold no golden matrices.  The oracle is
-pinned to the reference's three known-answer tests, to an autodiff restatement (oracle_ad.py) and
-to the analytic Laplace solution (see tests/test_oracle_pins.py).
+PARITY PIN STATUS (round 2): pinned against OUTPUTS OF THE REFERENCE'S OWN CODE.  The reference needs jax / jaxlib /
+lineax, none of which exist in this image; oracle/refshim/ supplies stand-ins for exactly the API surface its hot path
+touches (torch float64 underneath), with which the unmodified package /root/reference/updes imports and runs here --
+its own three tests pass (tests/test_reference_golden.py::test_reference_own_tests_pass_over_the_stand_in).  Golden
+vectors produced that way (tests/golden/ref_*.npz, generator tests/golden/make_reference_golden.py) pin this oracle:
+clouds bit for bit (SquareCloud incl. periodic groups; GmshCloud on the reference's mesh.msh incl. computed normals),
+every block of diffMat and A for all five kernels up to max_degree 4 to < 2e-15 row-scaled (1e-12 asserted), Robin +
+Neumann facets together (quirk Q3), periodic rows, the field evaluators, and the inv + GEMM + QR solutions.  What is
+NOT pinned: bit-for-bit agreement with XLA's CPU arithmetic (the stand-in computes with torch; both are IEEE double
+with LAPACK factorisations).  Older pins stay: the reference's three known-answer tests restated, an autodiff
+restatement (oracle_ad.py), mpmath 50-digit jets, the analytic Laplace solution (tests/test_oracle_pins.py).
 """
 from __future__ import annotations
 

@@ -1,0 +1,223 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE (run from the repo root in the build container, where
+/root/reference is mounted):
+
+    python tests/golden/make_reference_golden.py [--only NAME] [--out DIR]
+
+`import updes` below imports the unmodified reference package from /root/reference.  Its third-party dependencies
+(jax, lineax, matplotlib, seaborn) are absent from the image; oracle/refshim/ provides stand-ins for exactly the
+API surface the hot path touches, on torch float64 (see oracle/refshim/README.md for what that does and does not
+pin).  Every array written here is the return value of a reference function -- SquareCloud / GmshCloud,
+assemble_A, assemble_op_Phi_P, assemble_bd_Phi_P, assemble_q, pde_solver_jit -- called the way the reference's
+README, demos and tests call them.
+
+Files (tests/golden/ref_*.npz), each with the cloud arrays and:
+  ref_laplace_12x9        README problem (config 1 shape): A, opPhi, opP, bdPhi, bdP, q, B (= sol.mat), vals, coeffs
+  ref_robin_11x8          Neumann + Robin facets together (quirk Q3), gaussian eps=3, degree 2, operator with value,
+                          gradient and Laplacian terms, Robin (value, beta) tuples with callables
+  ref_periodic_10x10      config 2 shape: doubly periodic advection-diffusion, one implicit step with rhs = value(u)/DT
+  ref_kernels_7x6         all five kernels with max_degree 4 (15 monomials) and a field-dependent operator that
+                          uses every term of the set incl. nodal_div_grad; field evaluators value / gradient / laplacian
+  ref_config1_30x20       config 1 at full size: q, vals, coeffs, a row sample of B
+  ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
+                          sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
+                          rows with the reference's computed normals)
+"""
+import argparse
+import os
+import sys
+import time
+import warnings
+from functools import partial
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+sys.path.insert(0, REFERENCE)
+warnings.filterwarnings("ignore", message="The use of `x.T` on tensors")
+
+import jax.numpy as jnp  # noqa: E402  (the stand-in)
+import updes  # noqa: E402  (the reference itself)
+
+assert os.path.realpath(updes.__file__).startswith(REFERENCE), "must import the reference package, found %s" % updes.__file__
+
+
+def npa(t):
+    return np.asarray(t.detach().numpy() if hasattr(t, "detach") else t)
+
+
+def cloud_arrays(c):
+    """Same keys as tests/golden/make_golden.py so tests/helpers.py:cloud_from_golden can rebuild the cloud."""
+    names = list(c.facet_nodes.keys())
+    normals = npa(c.sorted_outward_normals) if hasattr(c, "sorted_outward_normals") else np.zeros((0, 2))
+    return dict(sorted_nodes=npa(c.sorted_nodes), sorted_outward_normals=normals,
+                counts=np.array([c.N, c.Ni, c.Nd, c.Nn, c.Nr]), Np=np.array(list(c.Np), dtype=np.int64),
+                facet_names=np.array(names), facet_sizes=np.array([len(c.facet_nodes[k]) for k in names]),
+                facet_nodes=np.concatenate([np.asarray(c.facet_nodes[k], dtype=np.int64) for k in names]),
+                facet_types=np.array([c.facet_types[k] for k in names]),
+                old_of_new=np.array([o for o, _ in sorted(c.renumbering_map.items(), key=lambda kv: kv[1])], dtype=np.int64),
+                supports_first_rows=npa(c.sorted_local_supports[:4]))
+
+
+def blocks(diff_operator, cloud, rbf, max_degree, diff_args, robin_coeffs):
+    """The four blocks of diffMat exactly as assemble_B builds them (assembly.py:384-385), plus A (:62-85)."""
+    M = updes.compute_nb_monomials(max_degree, cloud.dim)
+    opPhi, opP = updes.assemble_op_Phi_P(diff_operator, cloud, rbf, M, diff_args)
+    bdPhi, bdP = updes.assemble_bd_Phi_P(cloud, rbf, M, robin_coeffs)
+    A = updes.assemble_A(cloud, rbf, M)
+    return dict(opPhi=npa(opPhi), opP=npa(opP), bdPhi=npa(bdPhi), bdP=npa(bdP), A=npa(A), M=np.array(M))
+
+
+def solve(diff_operator, rhs_operator, cloud, bcs, rbf, max_degree, diff_args=None, rhs_args=None):
+    """pde_solver_jit as a user calls it (operators.py:650-683), plus q and the Robin coefficients it derives."""
+    sol = updes.pde_solver_jit(diff_operator=diff_operator, rhs_operator=rhs_operator, cloud=cloud, boundary_conditions=bcs,
+                               rbf=rbf, max_degree=max_degree, diff_args=diff_args, rhs_args=rhs_args)
+    bc_arr = updes.boundary_conditions_func_to_arr(bcs, cloud)
+    robin, bc_arr = updes.duplicate_robin_coeffs(bc_arr, cloud)
+    bc_arr = updes.zerofy_periodic_cond(bc_arr, cloud)
+    M = updes.compute_nb_monomials(max_degree, cloud.dim)
+    q = updes.assemble_q(rhs_operator, bc_arr, cloud, rbf, M, rhs_args)
+    betas = np.array([float(robin[k]) for k in sorted(robin)]) if robin else np.zeros(0)
+    return dict(vals=npa(sol.vals), coeffs=npa(sol.coeffs), B=npa(sol.mat), q=npa(q), betas=betas), robin
+
+
+# ---- cases -----------------------------------------------------------------------------------------------
+def laplace_op(x, center, rbf, monomial, fields):
+    return updes.nodal_laplacian(x, center, rbf, monomial)
+
+
+def zero_rhs(x, centers, rbf, fields):
+    return 0.0
+
+
+def case_laplace(nx, ny, keep_blocks=True):
+    cloud = updes.SquareCloud(Nx=nx, Ny=ny, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+    bcs = {"South": lambda c: 0.0, "West": lambda c: 0.0, "North": lambda c: jnp.sin(jnp.pi * c[0]), "East": lambda c: 0.0}
+    out, robin = solve(laplace_op, zero_rhs, cloud, bcs, updes.polyharmonic, 1)
+    if keep_blocks:
+        out.update(blocks(laplace_op, cloud, updes.polyharmonic, 1, None, robin))
+    else:
+        rows = np.arange(0, cloud.N, 37)
+        out["B_rows"], out["B_sample"] = rows, out.pop("B")[rows]
+    out.update(cloud_arrays(cloud))
+    return out
+
+
+def case_robin():
+    cloud = updes.SquareCloud(Nx=11, Ny=8, facet_types={"South": "n", "West": "r", "North": "d", "East": "r"})
+    rbf = partial(updes.gaussian, eps=3.0)
+
+    def op(x, center, rbf, monomial, fields):
+        val = updes.nodal_value(x, center, rbf, monomial)
+        grad = updes.nodal_gradient(x, center, rbf, monomial)
+        lap = updes.nodal_laplacian(x, center, rbf, monomial)
+        return 2.5 * val + jnp.dot(jnp.array([1.5, -0.5]), grad) - 0.3 * lap
+
+    def rhs(x, centers, rbf, fields):
+        return jnp.cos(3.0 * x[0]) * x[1]
+
+    bcs = {"South": lambda c: 0.25 * c[0], "West": (lambda c: 1.0 + c[1], lambda c: 2.0 + c[1]),
+           "North": lambda c: jnp.sin(jnp.pi * c[0]), "East": (lambda c: -0.5, 0.75 * jnp.ones(6))}
+    out, robin = solve(op, rhs, cloud, bcs, rbf, 2)
+    out.update(blocks(op, cloud, rbf, 2, None, robin))
+    out.update(cloud_arrays(cloud))
+    return out
+
+
+def case_periodic():
+    DT, VEL, K = 1e-4, (100.0, 0.0), 0.08
+    cloud = updes.SquareCloud(Nx=10, Ny=10, facet_types={"South": "p1", "North": "p1", "West": "p2", "East": "p2"})
+    rbf = partial(updes.polyharmonic, a=1)
+
+    def op(x, center, rbf, monomial, fields):
+        val = updes.nodal_value(x, center, rbf, monomial)
+        grad = updes.nodal_gradient(x, center, rbf, monomial)
+        lap = updes.nodal_laplacian(x, center, rbf, monomial)
+        return (val / DT) + jnp.dot(jnp.array(VEL), grad) - K * lap
+
+    def rhs(x, centers, rbf, fields):
+        return updes.value(x, fields[:, 0], centers, rbf) / DT
+
+    xy = npa(cloud.sorted_nodes)
+    u0 = np.exp(-((xy[:, 0] - 0.35) ** 2 + (xy[:, 1] - 0.5) ** 2) / (2 * 0.1 ** 2))
+    bcs = {k: (lambda c: 0.0) for k in cloud.facet_types}
+    out, robin = solve(op, rhs, cloud, bcs, rbf, 0, rhs_args=[jnp.array(u0)])
+    out.update(blocks(op, cloud, rbf, 0, None, robin))
+    out.update(u0=u0, **cloud_arrays(cloud))
+    return out
+
+
+KERNELS = [("polyharmonic", "a", 2), ("thin_plate", "a", 1), ("gaussian", "eps", 4.0), ("multiquadric", "eps", 2.0),
+           ("inverse_multiquadric", "eps", 1.5)]
+
+
+def case_kernels():
+    cloud = updes.SquareCloud(Nx=7, Ny=6, facet_types={"South": "n", "West": "d", "North": "d", "East": "n"})
+    xy = npa(cloud.sorted_nodes)
+    f0, f1 = 1.0 + xy[:, 0] * xy[:, 1], np.cos(2.0 * xy[:, 0]) - xy[:, 1]
+
+    def op(x, center, rbf, monomial, fields):
+        val = updes.nodal_value(x, center, rbf, monomial)
+        grad = updes.nodal_gradient(x, center, rbf, monomial)
+        lap = updes.nodal_laplacian(x, center, rbf, monomial)
+        dg = updes.nodal_div_grad(x, center, rbf, monomial, (fields[0], fields[1]))
+        return fields[0] * val + jnp.dot(jnp.array([fields[1], 0.3]), grad) - 0.7 * lap + dg
+
+    out = dict(f0=f0, f1=f1, **cloud_arrays(cloud))
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([xy[[0, 5, 17, 30, 41]], rng.uniform(0.05, 0.95, size=(6, 2))])     # nodes (r = 0 terms) and free points
+    out["eval_pts"] = pts
+    for name, pname, pval in KERNELS:
+        rbf = partial(getattr(updes, name), **{pname: pval})
+        b = blocks(op, cloud, rbf, 4, [jnp.array(f0), jnp.array(f1)], {})
+        for k in ("opPhi", "opP", "bdPhi", "bdP", "A"):
+            out["%s_%s" % (name, k)] = b[k]
+        coeffs = jnp.array(rng.normal(size=cloud.N + 15))
+        out["%s_coeffs" % name] = npa(coeffs)
+        out["%s_value" % name] = npa(updes.value_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
+        out["%s_gradient" % name] = npa(updes.gradient_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
+        out["%s_laplacian" % name] = npa(updes.laplacian_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
+    out["kernel_names"] = np.array([k[0] for k in KERNELS])
+    out["kernel_params"] = np.array([float(k[2]) for k in KERNELS])
+    return out
+
+
+MESH_FACETS = {"vel": {"Wall": "d", "Inflow": "d", "Outflow": "n", "Blowing": "d", "Suction": "d"},
+               "phi": {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"}}
+
+
+def case_mesh(tag):
+    cloud = updes.GmshCloud(filename=os.path.join(REFERENCE, "updes/tests/data/mesh.msh"), facet_types=MESH_FACETS[tag])
+    out = cloud_arrays(cloud)
+    if tag == "phi":
+        # boundary rows only (assembly.py:141-362): Dirichlet + Neumann rows with the normals GmshCloud computed
+        bdPhi, bdP = updes.assemble_bd_Phi_P(cloud, updes.polyharmonic, 3, {})
+        rows = np.arange(0, bdPhi.shape[0], 9)
+        out.update(bd_rows=rows, bdPhi_sample=npa(bdPhi)[rows], bdP_sample=npa(bdP)[rows])
+    return out
+
+
+CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
+         "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
+         "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default=HERE)
+    args = ap.parse_args()
+    for name, fn in CASES.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        t0 = time.time()
+        out = fn()
+        np.savez_compressed(os.path.join(args.out, name + ".npz"), **out)
+        print("%-22s %6.1f s  %d arrays  %.0f KB" % (name, time.time() - t0, len(out),
+                                                     os.path.getsize(os.path.join(args.out, name + ".npz")) / 1e3), flush=True)
+
+
+if __name__ == "__main__":
+    main()

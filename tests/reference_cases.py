@@ -1,0 +1,124 @@
+"""The problems of tests/golden/make_reference_golden.py written against the PRODUCT's call surface (``lib`` =
+updes_b200), plus what each lowers to.  The golden files hold what the reference's own code returned for the same
+problems; CPU tests compare the oracle and the product's host layer with them, GPU tests the CUDA path."""
+import os
+from functools import partial
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_K(g):
+    """[[opPhi opP], [bdPhi bdP], [P^T 0]] composed from the reference's blocks (the P^T rows are A's, assembly.py:80-83)."""
+    N, M = g["opPhi"].shape[1], int(g["M"])
+    top = np.concatenate([g["opPhi"], g["opP"]], axis=1)
+    mid = np.concatenate([g["bdPhi"], g["bdP"]], axis=1)
+    return np.concatenate([top, mid, g["A"][N:, :N + M]], axis=0)
+
+
+def facet_dict(g):
+    names = [str(v) for v in g["facet_names"]]
+    offs = np.concatenate([[0], np.cumsum(g["facet_sizes"])])
+    return {nm: g["facet_nodes"][offs[k]:offs[k + 1]].tolist() for k, nm in enumerate(names)}
+
+
+def assert_cloud_equals_golden(cloud, g):
+    """Every array the assembly reads from the cloud, bit for bit."""
+    assert np.array_equal(np.asarray(cloud.sorted_nodes), g["sorted_nodes"])
+    son = np.asarray(cloud.sorted_outward_normals, dtype=np.float64).reshape(-1, 2)
+    assert np.array_equal(son, g["sorted_outward_normals"].reshape(-1, 2))
+    assert [cloud.N, cloud.Ni, cloud.Nd, cloud.Nn, cloud.Nr] == g["counts"].tolist()
+    assert list(cloud.Np) == g["Np"].tolist()
+    want = facet_dict(g)
+    assert list(cloud.facet_nodes.keys()) == list(want.keys())
+    for k in want:
+        assert list(cloud.facet_nodes[k]) == want[k], k
+    assert [cloud.facet_types[k] for k in want] == [str(t) for t in g["facet_types"]]
+
+
+# ---- the four solved problems -------------------------------------------------------------------------------------
+class Case:
+    pass
+
+
+def laplace(lib, nx, ny):
+    c = Case()
+    c.cloud_args = dict(Nx=nx, Ny=ny, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+    c.kind, c.param, c.max_degree = "polyharmonic", 1, 1
+    c.rbf = lib.polyharmonic
+    c.op = lambda x, center, rbf, monomial, fields: lib.nodal_laplacian(x, center, rbf, monomial)
+    c.rhs = lambda x, centers, rbf, fields: 0.0
+    c.bcs = {"South": lambda p: 0.0, "West": lambda p: 0.0, "North": lambda p: np.sin(np.pi * p[0]), "East": lambda p: 0.0}
+    c.coef = lambda cloud: np.tile([0.0, 0.0, 0.0, 1.0, 1.0], (cloud.Ni, 1))
+    c.diff_args = c.rhs_args = None
+    return c
+
+
+def robin(lib):
+    c = Case()
+    c.cloud_args = dict(Nx=11, Ny=8, facet_types={"South": "n", "West": "r", "North": "d", "East": "r"})
+    c.kind, c.param, c.max_degree = "gaussian", 3.0, 2
+    c.rbf = partial(lib.gaussian, eps=3.0)
+
+    def op(x, center, rbf, monomial, fields):
+        val = lib.nodal_value(x, center, rbf, monomial)
+        grad = lib.nodal_gradient(x, center, rbf, monomial)
+        lap = lib.nodal_laplacian(x, center, rbf, monomial)
+        return 2.5 * val + lib.dot(np.array([1.5, -0.5]), grad) - 0.3 * lap
+    c.op = op
+    c.rhs = lambda x, centers, rbf, fields: np.cos(3.0 * x[0]) * x[1]
+    c.bcs = {"South": lambda p: 0.25 * p[0], "West": (lambda p: 1.0 + p[1], lambda p: 2.0 + p[1]),
+             "North": lambda p: np.sin(np.pi * p[0]), "East": (lambda p: -0.5, 0.75 * np.ones(6))}
+    c.coef = lambda cloud: np.tile([2.5, 1.5, -0.5, -0.3, -0.3], (cloud.Ni, 1))
+    c.diff_args = c.rhs_args = None
+    return c
+
+
+def periodic(lib, u0=None):
+    DT, VEL, K = 1e-4, (100.0, 0.0), 0.08
+    c = Case()
+    c.cloud_args = dict(Nx=10, Ny=10, facet_types={"South": "p1", "North": "p1", "West": "p2", "East": "p2"})
+    c.kind, c.param, c.max_degree = "polyharmonic", 1, 0
+    c.rbf = partial(lib.polyharmonic, a=1)
+
+    def op(x, center, rbf, monomial, fields):
+        val = lib.nodal_value(x, center, rbf, monomial)
+        grad = lib.nodal_gradient(x, center, rbf, monomial)
+        lap = lib.nodal_laplacian(x, center, rbf, monomial)
+        return (val / DT) + lib.dot(np.asarray(VEL), grad) - K * lap
+    c.op = op
+    c.rhs = lambda x, centers, rbf, fields: lib.value(x, fields[:, 0], centers, rbf) / DT
+    c.bcs = {k: (lambda p: 0.0) for k in c.cloud_args["facet_types"]}
+    c.coef = lambda cloud: np.tile([1.0 / DT, VEL[0], VEL[1], -K, -K], (cloud.Ni, 1))
+    c.diff_args, c.rhs_args = None, (None if u0 is None else [u0])
+    return c
+
+
+def kernels_operator(lib):
+    """Uses every term of the set with field-dependent coefficients (fields = f0, f1 of the golden file):
+    f0 phi + f1 phi_x + 0.3 phi_y + (f0 - 0.7) phi_xx + (f1 - 0.7) phi_yy."""
+    def op(x, center, rbf, monomial, fields):
+        val = lib.nodal_value(x, center, rbf, monomial)
+        grad = lib.nodal_gradient(x, center, rbf, monomial)
+        lap = lib.nodal_laplacian(x, center, rbf, monomial)
+        dg = lib.nodal_div_grad(x, center, rbf, monomial, (fields[0], fields[1]))
+        return fields[0] * val + lib.dot([fields[1], 0.3], grad) - 0.7 * lap + dg
+    return op
+
+
+def kernels_coef(g, Ni):
+    f0, f1 = g["f0"][:Ni], g["f1"][:Ni]
+    return np.stack([f0, f1, np.full(Ni, 0.3), f0 - 0.7, f1 - 0.7], axis=1)
+
+
+KERNELS_CLOUD = dict(Nx=7, Ny=6, facet_types={"South": "n", "West": "d", "North": "d", "East": "n"})
+
+
+def kernel_rbf(lib, name, param):
+    f = getattr(lib, name)
+    return partial(f, a=int(param)) if name in ("polyharmonic", "thin_plate") else partial(f, eps=float(param))

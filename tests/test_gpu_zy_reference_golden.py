@@ -1,0 +1,141 @@
+"""GPU parity against golden vectors produced by the REFERENCE'S OWN CODE (tests/golden/ref_*.npz; see
+tests/golden/make_reference_golden.py and oracle/refshim/README.md): the CUDA assembly, the field evaluators and the
+whole pde_solver path, through the public API and the C-ABI, on the same problems the reference solved.
+Tolerances are the north_star's: matrix entries 1e-12 relative (row-scale floor; true per-entry error reported and
+bounded too), solutions 1e-8 relative or the cond-scaled backward-error clause."""
+import numpy as np
+import pytest
+
+import updes_b200 as u
+from updes_b200 import assembly as asm
+import reference_cases as rc
+from helpers import backward_error, exact_solution, rel_err_rowscaled, true_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _assemble(cloud, table, kind, param, M):
+    rows = asm.DeviceRows(cloud, table)
+    K = asm.assemble_system(rows, kind, param, M).cpu().numpy()
+    n = cloud.N + M
+    assert np.all(K[:, n:] == 0.0)
+    return K[:, :n]
+
+
+def _check_matrices(cloud, g, kind, param, coef, betas=None, prefix=""):
+    """K = [[opPhi opP], [bdPhi bdP], [P^T 0]] and A = [[Phi P], [P^T 0]] against the reference's blocks."""
+    M = g[prefix + "opP"].shape[1]
+    N = cloud.N
+    want_K = np.concatenate([np.concatenate([g[prefix + "opPhi"], g[prefix + "opP"]], axis=1),
+                             np.concatenate([g[prefix + "bdPhi"], g[prefix + "bdP"]], axis=1),
+                             g[prefix + "A"][N:, :N + M]], axis=0)
+    got_K = _assemble(cloud, asm.build_operator_rows(cloud, coef, None, betas), kind, param, M)
+    got_A = _assemble(cloud, asm.build_interpolation_rows(cloud), kind, param, M)
+    for what, got, want in (("K", got_K, want_K), ("A", got_A, g[prefix + "A"])):
+        e, t = rel_err_rowscaled(got, want), true_rel_err(got, want)
+        print("%s%s: row-scaled %.1e, true per-entry %.1e" % (prefix, what, e, t))
+        assert e <= 1e-12, (prefix, what, e)
+        assert t <= 2e-10, (prefix, what, t)
+
+
+def _check_solution(sol, g, M, what):
+    """(1) backward error of the product's coefficients on the REFERENCE's matrix <= 1e-13; (2) product vs the exactly
+    solved discrete system <= 1e-8; (3) product vs the reference's vals <= 1e-8, or 4x the reference's own distance
+    from that exact solution where inv(A) + QR lost more than that."""
+    K = rc.golden_K(g)
+    N = K.shape[1] - M
+    rhs = np.concatenate([g["q"], np.zeros(M)])
+    exact, _ = exact_solution(K, rhs, g["A"][:N])
+    scale = np.max(np.abs(exact))
+    e_prod = np.max(np.abs(sol.vals - exact)) / scale
+    e_gold = np.max(np.abs(g["vals"] - exact)) / scale
+    d = np.max(np.abs(sol.vals - g["vals"])) / scale
+    berr = backward_error(K, sol.coeffs, rhs)
+    print("%s: product-vs-exact %.2e  reference-vs-exact %.2e  product-vs-reference %.2e  backward error %.2e" % (what, e_prod, e_gold, d, berr))
+    assert berr <= 1e-13, (what, berr)
+    assert e_prod <= 1e-8, (what, e_prod)
+    assert d <= max(1e-8, 4.0 * e_gold), (what, d, e_gold)
+
+
+@pytest.mark.parametrize("name,nx,ny", [("ref_laplace_12x9", 12, 9)])
+def test_laplace_matrices_and_solution(name, nx, ny):
+    g = rc.load(name)
+    case = rc.laplace(u, nx, ny)
+    cloud = u.SquareCloud(**case.cloud_args)
+    rc.assert_cloud_equals_golden(cloud, g)
+    _check_matrices(cloud, g, case.kind, case.param, case.coef(cloud))
+    sol = u.pde_solver_jit(diff_operator=case.op, rhs_operator=case.rhs, cloud=cloud, boundary_conditions=case.bcs, rbf=case.rbf,
+                           max_degree=case.max_degree)
+    _check_solution(sol, g, 3, name)
+    assert np.max(np.abs(sol.mat - g["B"])) <= 1e-6 * np.max(np.abs(g["B"]))          # SteadySol.mat is the reference's B
+
+
+def test_robin_and_neumann_facets_with_the_normal_quirk():
+    g = rc.load("ref_robin_11x8")
+    case = rc.robin(u)
+    cloud = u.SquareCloud(**case.cloud_args)
+    rc.assert_cloud_equals_golden(cloud, g)
+    _check_matrices(cloud, g, case.kind, case.param, case.coef(cloud), betas=g["betas"])
+    sol = u.pde_solver_jit(diff_operator=case.op, rhs_operator=case.rhs, cloud=cloud, boundary_conditions=case.bcs, rbf=case.rbf,
+                           max_degree=case.max_degree)
+    _check_solution(sol, g, 6, "robin")
+
+
+def test_periodic_advection_diffusion_step():
+    g = rc.load("ref_periodic_10x10")
+    case = rc.periodic(u, u0=g["u0"])
+    cloud = u.SquareCloud(**case.cloud_args)
+    rc.assert_cloud_equals_golden(cloud, g)
+    _check_matrices(cloud, g, case.kind, case.param, case.coef(cloud))
+    sol = u.pde_solver_jit(diff_operator=case.op, rhs_operator=case.rhs, rhs_args=case.rhs_args, cloud=cloud,
+                           boundary_conditions=case.bcs, rbf=case.rbf, max_degree=case.max_degree)
+    # the right-hand side the product built (coefficients of u0 through the LU of A, value(u0)/DT) against the reference's
+    bc_arr = u.zerofy_periodic_cond(u.boundary_conditions_func_to_arr(case.bcs, cloud), cloud)
+    q = u.assemble_q(case.rhs, bc_arr, cloud, case.rbf, 1, case.rhs_args)
+    assert np.max(np.abs(q - g["q"])) <= 1e-9 * np.max(np.abs(g["q"]))
+    _check_solution(sol, g, 1, "periodic")
+
+
+def test_all_kernels_degree4_and_field_evaluators():
+    g = rc.load("ref_kernels_7x6")
+    cloud = u.SquareCloud(**rc.KERNELS_CLOUD)
+    rc.assert_cloud_equals_golden(cloud, g)
+    op = rc.kernels_operator(u)
+    for name, param in zip(g["kernel_names"], g["kernel_params"]):
+        name = str(name)
+        rbf = rc.kernel_rbf(u, name, param)
+        coef, coef_pol = u.lower_diff_operator(op, cloud, rbf, [g["f0"], g["f1"]])
+        assert np.allclose(coef, rc.kernels_coef(g, cloud.Ni), rtol=1e-15, atol=0) and np.array_equal(coef, coef_pol)
+        _check_matrices(cloud, g, name, float(param), coef, prefix=name + "_")
+        cf, pts = g[name + "_coeffs"], g["eval_pts"]
+        v = u.value_vec(pts, cf, cloud.sorted_nodes, rbf)
+        gr = u.gradient_vec(pts, cf, cloud.sorted_nodes, rbf)
+        lp = u.laplacian_vec(pts, cf, cloud.sorted_nodes, rbf)
+        for what, got, want in (("value", v, g[name + "_value"]), ("gradient", gr, g[name + "_gradient"]), ("laplacian", lp, g[name + "_laplacian"])):
+            err = np.max(np.abs(np.asarray(got) - want)) / np.max(np.abs(want))
+            assert err <= 1e-10, (name, what, err)
+
+
+def test_config1_full_size_against_the_reference_solution():
+    g = rc.load("ref_config1_30x20")
+    case = rc.laplace(u, 30, 20)
+    cloud = u.SquareCloud(**case.cloud_args)
+    rc.assert_cloud_equals_golden(cloud, g)
+    sol = u.pde_solver_jit(diff_operator=case.op, rhs_operator=case.rhs, cloud=cloud, boundary_conditions=case.bcs, rbf=case.rbf,
+                           max_degree=case.max_degree)
+    assert np.max(np.abs(sol.vals - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))       # north_star: 1e-8 relative
+    rows = g["B_rows"]
+    assert np.max(np.abs(sol.mat[rows] - g["B_sample"])) <= 1e-6 * np.max(np.abs(g["B_sample"]))
+
+
+def test_gmsh_boundary_rows_on_the_reference_cloud():
+    """Neumann / Dirichlet rows on the reference's mesh.msh cloud (normals computed by the reference's GmshCloud)."""
+    from helpers import cloud_from_golden
+    g = rc.load("ref_mesh_msh_phi")
+    cloud, _ = cloud_from_golden("ref_mesh_msh_phi.npz")
+    coef = np.tile([0.0, 0.0, 0.0, 1.0, 1.0], (cloud.Ni, 1))
+    K = _assemble(cloud, asm.build_operator_rows(cloud, coef), "polyharmonic", 1, 3)
+    r = g["bd_rows"]
+    got = K[cloud.Ni + r]
+    want = np.concatenate([g["bdPhi_sample"], g["bdP_sample"]], axis=1)
+    assert rel_err_rowscaled(got, want) <= 1e-12

@@ -1,0 +1,222 @@
+"""CPU tests against golden vectors produced by the REFERENCE'S OWN CODE (tests/golden/ref_*.npz, written by
+tests/golden/make_reference_golden.py: the unmodified /root/reference package executed over the JAX-API stand-in of
+oracle/refshim/).  They pin (1) the oracle -- clouds bit for bit, every block of diffMat and A to 1e-12 per entry, the
+solve -- and (2) the product's host layer: clouds, operator lowering, boundary-condition preparation, right-hand side.
+The GPU counterpart (the CUDA path against the same files) is tests/test_gpu_zy_reference_golden.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import updes_b200 as u
+import reference_cases as rc
+from helpers import exact_solution, rel_err_rowscaled, true_rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+
+
+def _check_blocks(oracle, cloud, g, kind, param, coef, betas=None, prefix=""):
+    M = g[prefix + "opP"].shape[1]
+    A = oracle.assemble_A(cloud, kind, param, M)
+    opPhi, opP = oracle.assemble_op_Phi_P(cloud, kind, param, M, coef)
+    bdPhi, bdP = oracle.assemble_bd_Phi_P(cloud, kind, param, M, betas)
+    worst = 0.0
+    for name, got in (("A", A), ("opPhi", opPhi), ("opP", opP), ("bdPhi", bdPhi), ("bdP", bdP)):
+        want = g[prefix + name]
+        assert got.shape == want.shape, name
+        e, t = rel_err_rowscaled(got, want), true_rel_err(got, want)
+        assert e <= 1e-12, (name, e)           # north_star: 1e-12 relative per entry (row-scale floor)
+        assert t <= 1e-10, (name, t)           # true per-entry relative error where no cancellation
+        worst = max(worst, e)
+    return worst
+
+
+def _solution_close(vals, g, K, rhs, A_rows, what):
+    """Two inverse-based pipelines (the reference's over torch LAPACK, the oracle's over scipy LAPACK) agree to the
+    accuracy either has: 1e-8, or 4x the golden solution's own distance from the exactly solved discrete system."""
+    exact, _ = exact_solution(K, rhs, A_rows)
+    scale = np.max(np.abs(exact))
+    e_gold = np.max(np.abs(g["vals"] - exact)) / scale
+    d = np.max(np.abs(vals - g["vals"])) / scale
+    print("%s: golden-vs-exact %.2e, ours-vs-golden %.2e" % (what, e_gold, d))
+    assert d <= max(1e-8, 4.0 * e_gold), (what, d, e_gold)
+
+
+@pytest.mark.parametrize("name,nx,ny", [("ref_laplace_12x9", 12, 9)])
+def test_oracle_laplace_blocks_and_solution(oracle, name, nx, ny):
+    g = rc.load(name)
+    case = rc.laplace(u, nx, ny)
+    cloud = oracle.RefSquareCloud(nx, ny, case.cloud_args["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    coef = case.coef(cloud)
+    print("worst block error %.1e" % _check_blocks(oracle, cloud, g, case.kind, case.param, coef))
+    xy = cloud.sorted_nodes
+    bc = {f: (np.sin(np.pi * xy[ids, 0]) if f == "North" else np.zeros(len(ids))) for f, ids in cloud.facet_nodes.items()}
+    q = oracle.assemble_q(cloud, np.zeros(cloud.Ni), bc)
+    assert np.array_equal(q, g["q"])
+    vals, coeffs, B = oracle.reference_solve(cloud, case.kind, case.param, case.max_degree, coef, q)
+    assert np.max(np.abs(B - g["B"])) <= 1e-9 * np.max(np.abs(g["B"]))            # B = diffMat inv(A)[:, :N] (assembly.py:396-401)
+    K = rc.golden_K(g)
+    _solution_close(vals, g, K, np.concatenate([q, np.zeros(3)]), g["A"][:cloud.N], name)
+
+
+def test_oracle_robin_with_neumann_quirk_q3(oracle):
+    """Neumann and Robin facets together: the reference's bd(Phi) reads normals[i-Ni-Nd-Nn] (assembly.py:206) -- the
+    golden rows carry that quirk because the reference's code produced them."""
+    g = rc.load("ref_robin_11x8")
+    case = rc.robin(u)
+    cloud = oracle.RefSquareCloud(11, 8, case.cloud_args["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert cloud.Nn > 0 and cloud.Nr > 0
+    _check_blocks(oracle, cloud, g, case.kind, case.param, case.coef(cloud), betas=g["betas"])
+    vals, _, B = oracle.reference_solve(cloud, case.kind, case.param, case.max_degree, case.coef(cloud), g["q"], betas=g["betas"])
+    assert np.max(np.abs(B - g["B"])) <= 1e-9 * np.max(np.abs(g["B"]))
+    M = int(g["M"])
+    _solution_close(vals, g, rc.golden_K(g), np.concatenate([g["q"], np.zeros(M)]), g["A"][:cloud.N], "robin")
+
+
+def test_oracle_periodic_advection_diffusion_step(oracle):
+    g = rc.load("ref_periodic_10x10")
+    case = rc.periodic(u)
+    cloud = oracle.RefSquareCloud(10, 10, case.cloud_args["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert list(cloud.Np) == [20, 16]
+    coef = case.coef(cloud)
+    _check_blocks(oracle, cloud, g, case.kind, case.param, coef)
+    # right-hand side value(u0)/DT on internal nodes (operators.py:118-147 through assembly.py:455-468)
+    A = oracle.assemble_A(cloud, case.kind, case.param, 1)
+    cprev = np.linalg.solve(A, np.concatenate([g["u0"], np.zeros(1)]))
+    q_int = oracle.eval_field(cloud.sorted_nodes[:cloud.Ni], cloud.sorted_nodes, cprev, case.kind, case.param, "value") / 1e-4
+    q = oracle.assemble_q(cloud, q_int, {k: np.zeros(len(cloud.facet_nodes[k])) for k in cloud.facet_types})
+    assert np.max(np.abs(q - g["q"])) <= 1e-10 * np.max(np.abs(g["q"]))
+    vals, _, _ = oracle.reference_solve(cloud, case.kind, case.param, case.max_degree, coef, g["q"])
+    _solution_close(vals, g, rc.golden_K(g), np.concatenate([g["q"], np.zeros(1)]), g["A"][:cloud.N], "periodic")
+
+
+def test_oracle_all_kernels_degree4_and_field_evaluators(oracle):
+    """All five kernels, 15 monomials, an operator with every term of the set (incl. nodal_div_grad) and
+    field-dependent coefficients; value / gradient / laplacian of a random coefficient vector at nodes (r = 0 terms,
+    nan_to_num) and free points."""
+    g = rc.load("ref_kernels_7x6")
+    cloud = oracle.RefSquareCloud(7, 6, rc.KERNELS_CLOUD["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    coef = rc.kernels_coef(g, cloud.Ni)
+    for name, param in zip(g["kernel_names"], g["kernel_params"]):
+        name = str(name)
+        _check_blocks(oracle, cloud, g, name, param, coef, prefix=name + "_")
+        cf, pts = g[name + "_coeffs"], g["eval_pts"]
+        for which, want in (("value", g[name + "_value"]), ("dx", g[name + "_gradient"][:, 0]), ("dy", g[name + "_gradient"][:, 1]),
+                            ("laplacian", g[name + "_laplacian"])):
+            got = oracle.eval_field(pts, cloud.sorted_nodes, cf, name, param, which)
+            assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)), (name, which)
+
+
+def test_oracle_config1_full_size_solution(oracle):
+    """Config 1 at full size (30x20): the reference's own pde_solver_jit result."""
+    g = rc.load("ref_config1_30x20")
+    old = np.load(os.path.join(rc.GOLDEN, "config1_30x20_phs3.npz"))
+    case = rc.laplace(u, 30, 20)
+    cloud = oracle.RefSquareCloud(30, 20, case.cloud_args["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert np.array_equal(g["q"], old["q"])
+    vals, coeffs, B = oracle.reference_solve(cloud, case.kind, case.param, 1, case.coef(cloud), g["q"])
+    assert np.max(np.abs(B[g["B_rows"]] - g["B_sample"])) <= 1e-8 * np.max(np.abs(g["B_sample"]))
+    assert np.max(np.abs(vals - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))          # north_star: 1e-8 relative
+    assert np.max(np.abs(old["vals"] - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))   # the round-1 oracle-made fixture
+    xy = g["sorted_nodes"]
+    exact = np.sin(np.pi * xy[:, 0]) * np.cosh(np.pi * xy[:, 1]) / np.cosh(np.pi)
+    assert np.max(np.abs(g["vals"] - exact)) <= 2e-2                                         # demos/Laplace/00_...:109-110
+
+
+@pytest.mark.parametrize("tag", ["vel", "phi"])
+def test_gmsh_cloud_of_the_reference_equals_the_restatement(oracle, tag):
+    """The reference's GmshCloud on its own fixture mesh.msh: nodes, renumbering, facet lists and the computed
+    outward normals equal the oracle-made fixtures the GPU tests use (tests/golden/mesh_msh_cloud_*.npz), bit for bit;
+    boundary rows (Neumann rows with those normals) to 1e-12."""
+    g = rc.load("ref_mesh_msh_" + tag)
+    old = np.load(os.path.join(rc.GOLDEN, "mesh_msh_cloud_%s.npz" % tag))
+    for k in ("sorted_nodes", "sorted_outward_normals", "counts", "Np", "facet_names", "facet_sizes", "facet_nodes", "facet_types", "old_of_new"):
+        assert np.array_equal(g[k], old[k]), k
+    if tag == "phi":
+        from helpers import cloud_from_golden
+        cloud, _ = cloud_from_golden("mesh_msh_cloud_phi.npz")
+        bdPhi, bdP = oracle.assemble_bd_Phi_P(cloud, "polyharmonic", 1, 3)
+        r = g["bd_rows"]
+        assert rel_err_rowscaled(bdPhi[r], g["bdPhi_sample"]) <= 1e-12 and rel_err_rowscaled(bdP[r], g["bdP_sample"]) <= 1e-12
+
+
+# ---- the product's host layer against the same files -----------------------------------------------------------------
+def test_product_clouds_lowering_and_bc_preparation_match_the_reference():
+    for name, case in (("ref_laplace_12x9", rc.laplace(u, 12, 9)), ("ref_robin_11x8", rc.robin(u)),
+                       ("ref_periodic_10x10", rc.periodic(u)), ("ref_config1_30x20", rc.laplace(u, 30, 20))):
+        g = rc.load(name)
+        cloud = u.SquareCloud(**case.cloud_args)
+        rc.assert_cloud_equals_golden(cloud, g)
+        coef_phi, coef_pol = u.lower_diff_operator(case.op, cloud, case.rbf, case.diff_args)
+        assert np.allclose(coef_phi, case.coef(cloud), rtol=1e-15, atol=0) and np.array_equal(coef_phi, coef_pol), name
+        # boundary-condition preparation (operators.py:512-555, :628-647): Robin betas per node, arrays per facet
+        bc_arr = u.boundary_conditions_func_to_arr(case.bcs, cloud)
+        robin, bc_arr = u.duplicate_robin_coeffs(dict(bc_arr), cloud)
+        betas = np.array([robin[k] for k in sorted(robin)], dtype=np.float64) if robin else np.zeros(0)
+        assert np.allclose(betas, g["betas"], rtol=1e-15, atol=0), name
+        if name != "ref_periodic_10x10":               # (its right-hand side evaluates a field: GPU test)
+            bc_arr = u.zerofy_periodic_cond(bc_arr, cloud)
+            M = u.compute_nb_monomials(case.max_degree, 2)
+            q = u.assemble_q(case.rhs, bc_arr, cloud, case.rbf, M, None)
+            assert np.allclose(q, g["q"], rtol=1e-15, atol=1e-300), name
+    # kernels case: field-dependent coefficients through the symbolic lowering
+    g = rc.load("ref_kernels_7x6")
+    cloud = u.SquareCloud(**rc.KERNELS_CLOUD)
+    rc.assert_cloud_equals_golden(cloud, g)
+    coef_phi, coef_pol = u.lower_diff_operator(rc.kernels_operator(u), cloud, rc.kernel_rbf(u, "gaussian", 4.0), [g["f0"], g["f1"]])
+    assert np.allclose(coef_phi, rc.kernels_coef(g, cloud.Ni), rtol=1e-15, atol=0) and np.array_equal(coef_phi, coef_pol)
+
+
+def test_product_gmsh_reader_matches_the_reference_cloud(tmp_path):
+    """GmshCloud of the product on a copy of the fixture (the .msh file itself is reference data and is not committed:
+    only run where /root/reference is mounted)."""
+    mesh = os.path.join(REFERENCE, "updes/tests/data/mesh.msh")
+    if not os.path.exists(mesh):
+        pytest.skip("needs /root/reference (build container)")
+    for tag, ft in (("vel", {"Wall": "d", "Inflow": "d", "Outflow": "n", "Blowing": "d", "Suction": "d"}),
+                    ("phi", {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"})):
+        cloud = u.GmshCloud(filename=mesh, facet_types=ft)
+        rc.assert_cloud_equals_golden(cloud, rc.load("ref_mesh_msh_" + tag))
+
+
+# ---- the generator reproduces the committed files; the reference's own tests pass over the stand-in ------------------
+def _run(cmd, cwd, timeout):
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    return subprocess.run(cmd, cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_generator_reproduces_committed_goldens(tmp_path):
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("needs /root/reference (build container)")
+    r = _run([sys.executable, os.path.join(rc.GOLDEN, "make_reference_golden.py"), "--out", str(tmp_path),
+              "--only", "ref_robin_11x8,ref_periodic_10x10"], ROOT, 900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("ref_robin_11x8", "ref_periodic_10x10"):
+        new, old = np.load(str(tmp_path / (name + ".npz"))), rc.load(name)
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            if old[k].dtype.kind in "fc":
+                assert np.allclose(new[k], old[k], rtol=1e-13, atol=1e-13 * max(1.0, float(np.max(np.abs(old[k]))) if old[k].size else 1.0)), (name, k)
+            else:
+                assert np.array_equal(new[k], old[k]), (name, k)
+
+
+def test_reference_own_tests_pass_over_the_stand_in():
+    """updes/tests/test_{interpolation,integrals,operators}.py of the reference, unmodified, with oracle/refshim on the
+    path: the stand-in is faithful enough for the reference's own known-answer tests (constant-field gradient and
+    divergence on mesh.msh with a gaussian kernel, the pi/12 integral, the cloud-to-cloud permutation)."""
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("needs /root/reference (build container)")
+    env_path = os.path.join(ROOT, "oracle", "refshim")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-m", "pytest", "updes/tests/test_interpolation.py", "updes/tests/test_integrals.py",
+                        "updes/tests/test_operators.py", "-q", "-p", "no:cacheprovider"], cwd=REFERENCE,
+                       env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=env_path), capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
