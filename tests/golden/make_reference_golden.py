@@ -18,6 +18,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_kernels_7x6         all five kernels with max_degree 4 (15 monomials) and a field-dependent operator that
                           uses every term of the set incl. nodal_div_grad; field evaluators value / gradient / laplacian
   ref_config1_30x20       config 1 at full size: q, vals, coeffs, a row sample of B
+  ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
                           rows with the reference's computed normals)
@@ -199,9 +200,29 @@ def case_mesh(tag):
     return out
 
 
+def case_config3(nb_iter=2):
+    """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
+    is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
+    script builds its clouds with the gmsh package and plots); both clouds come from the reference's mesh.msh."""
+    import jax
+    from jax.tree_util import Partial
+    src = open(os.path.join(REFERENCE, "demos/NavierStokes/30_channel_flow_blowing_suction.py")).read()
+    body = src[src.index("def diff_operator_u("):src.index("def diff_operator_id(")]
+    ns = {k: getattr(updes, k) for k in dir(updes) if not k.startswith("_")}
+    ns.update(jax=jax, jnp=jnp, Partial=Partial, partial=partial, RBF=updes.polyharmonic, MAX_DEGREE=1, Re=100, Pa=0., NB_ITER=5)
+    exec(compile(body, "30_channel_flow_blowing_suction.py", "exec"), ns)
+    mesh = os.path.join(REFERENCE, "updes/tests/data/mesh.msh")
+    cloud_vel = updes.GmshCloud(filename=mesh, facet_types=MESH_FACETS["vel"])
+    cloud_phi = updes.GmshCloud(filename=mesh, facet_types=MESH_FACETS["phi"])
+    u_list, v_list, vel_list, p_list = ns["simulate_forward_navier_stokes"](cloud_vel, cloud_phi, NB_ITER=nb_iter)
+    return dict(u=np.stack([npa(x) for x in u_list]), v=np.stack([npa(x) for x in v_list]), p=np.stack([npa(x) for x in p_list]),
+                vel=np.stack([npa(x) for x in vel_list]), nb_iter=np.array(nb_iter), Re=np.array(100.0))
+
+
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
-         "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi")}
+         "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
+         "ref_config3_ns_2iter": case_config3}
 
 
 def main():

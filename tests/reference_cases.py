@@ -122,3 +122,33 @@ KERNELS_CLOUD = dict(Nx=7, Ny=6, facet_types={"South": "n", "West": "d", "North"
 def kernel_rbf(lib, name, param):
     f = getattr(lib, name)
     return partial(f, a=int(param)) if name in ("polyharmonic", "thin_plate") else partial(f, eps=float(param))
+
+
+def oracle_config3_loop(oracle, interpolate_field, bcs, cv, cp, nb_iter=2, Re=100.0, M=3):
+    """simulate_forward_navier_stokes (demos/NavierStokes/30_...:97-213) restated with the oracle's reference
+    formulation: inv(A) coefficients for the rhs fields, B = D inv(A), QR.  Returns [(u, v, p_)] after every iteration."""
+    bc_u, bc_v, bc_phi = bcs
+    Av, Ap = oracle.assemble_A(cv, "polyharmonic", 1, M), oracle.assemble_A(cp, "polyharmonic", 1, M)
+    coefs_of = lambda A, f: np.linalg.solve(A, np.concatenate([f, np.zeros(M)]))
+    ev = lambda cloud, c, which, pts=None: oracle.eval_field(cloud.sorted_nodes if pts is None else pts, cloud.sorted_nodes, c,
+                                                            "polyharmonic", 1, which)
+    ru, rv, rp_ = np.zeros(cv.N), np.zeros(cv.N), np.zeros(cp.N)
+    lap_coef = np.tile([0.0, 0, 0, 1.0, 1.0], (cp.Ni, 1))
+    out = []
+    for _ in range(nb_iter):
+        p = interpolate_field(rp_, cp, cv)
+        cpv = coefs_of(Av, p)
+        coef = np.stack([np.zeros(cv.Ni), ru[:cv.Ni], rv[:cv.Ni], np.full(cv.Ni, -1 / Re), np.full(cv.Ni, -1 / Re)], axis=1)
+        qu = oracle.assemble_q(cv, -ev(cv, cpv, "dx", cv.sorted_nodes[:cv.Ni]), bc_u)
+        qv = oracle.assemble_q(cv, -ev(cv, cpv, "dy", cv.sorted_nodes[:cv.Ni]), bc_v)
+        ustar, _, _ = oracle.reference_solve(cv, "polyharmonic", 1, 1, coef, qu)
+        vstar, _, _ = oracle.reference_solve(cv, "polyharmonic", 1, 1, coef, qv)
+        u_, v_ = interpolate_field(ustar, cv, cp), interpolate_field(vstar, cv, cp)
+        cu_, cv_ = coefs_of(Ap, u_), coefs_of(Ap, v_)
+        div = ev(cp, cu_, "dx", cp.sorted_nodes[:cp.Ni]) + ev(cp, cv_, "dy", cp.sorted_nodes[:cp.Ni])
+        phi, cphi, _ = oracle.reference_solve(cp, "polyharmonic", 1, 1, lap_coef, oracle.assemble_q(cp, div, bc_phi))
+        rp_ = rp_ + phi
+        gradphi = interpolate_field(np.stack([ev(cp, cphi, "dx"), ev(cp, cphi, "dy")], axis=-1), cp, cv)
+        ru, rv = ustar - gradphi[:, 0], vstar - gradphi[:, 1]
+        out.append((ru, rv, rp_))
+    return out

@@ -139,3 +139,24 @@ def test_gmsh_boundary_rows_on_the_reference_cloud():
     got = K[cloud.Ni + r]
     want = np.concatenate([g["bdPhi_sample"], g["bdP_sample"]], axis=1)
     assert rel_err_rowscaled(got, want) <= 1e-12
+
+
+def test_config3_projection_loop_against_the_reference_demo():
+    """Config 3 end to end: the product's projection loop (tools/configs.py, the demo's loop on the public API) against
+    what the reference's own demo code produced for the same two iterations (tests/golden/ref_config3_ns_2iter.npz).
+    The reference pipeline goes through inv(A) at cond ~ 1e9 in every solve and feeds results back, so the bound is
+    the cond-scaled one used for the oracle-formulation loop in tests/test_gpu_solver.py (oracle vs demo on CPU: 5e-6)."""
+    import configs_path  # noqa: F401
+    import configs
+    from helpers import cloud_from_golden
+    g = rc.load("ref_config3_ns_2iter")
+    cv, _ = cloud_from_golden("ref_mesh_msh_vel.npz")
+    cp, _ = cloud_from_golden("ref_mesh_msh_phi.npz")
+    uu, vv, p_, hist = configs.config3_projection_loop(u, cv, cp, nb_iter=int(g["nb_iter"]), Re=float(g["Re"]))
+    rel = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    worst = 0.0
+    for it, h in enumerate(hist):
+        for nm, got, want in (("u", h[3], g["u"][it + 1]), ("v", h[4], g["v"][it + 1]), ("p", h[5], g["p"][it + 1])):
+            worst = max(worst, rel(got, want))
+            print("iteration %d %s product-vs-reference-demo %.2e" % (it, nm, rel(got, want)))
+    assert worst <= 2e-5, worst

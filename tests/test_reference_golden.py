@@ -220,3 +220,24 @@ def test_reference_own_tests_pass_over_the_stand_in():
                         "updes/tests/test_operators.py", "-q", "-p", "no:cacheprovider"], cwd=REFERENCE,
                        env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=env_path), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_oracle_config3_projection_loop_matches_the_reference_demo(oracle):
+    """Config 3: two iterations of simulate_forward_navier_stokes as the reference's demo script itself runs it (its source
+    executed unchanged by the generator) against the oracle's restatement of the loop.  Every solve goes through
+    inv(A) at cond ~ 1e9 in both pipelines and feeds the next one, hence the cond-scaled bound (measured: 5e-6)."""
+    import configs_path  # noqa: F401
+    import configs
+    from helpers import cloud_from_golden
+    g = rc.load("ref_config3_ns_2iter")
+    cv, _ = cloud_from_golden("ref_mesh_msh_vel.npz")
+    cp, _ = cloud_from_golden("ref_mesh_msh_phi.npz")
+    hist = rc.oracle_config3_loop(oracle, u.interpolate_field, configs.config3_boundary_arrays(cv, cp), cv, cp, int(g["nb_iter"]))
+    rel = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    worst = 0.0
+    for it, (uu, vv, pp) in enumerate(hist):
+        for nm, got, want in (("u", uu, g["u"][it + 1]), ("v", vv, g["v"][it + 1]), ("p", pp, g["p"][it + 1])):
+            worst = max(worst, rel(got, want))
+            print("iteration %d %s oracle-vs-reference-demo %.2e" % (it, nm, rel(got, want)))
+    assert worst <= 2e-5, worst
+    assert np.abs(g["u"][-1]).max() > 0.5           # a developed channel flow
