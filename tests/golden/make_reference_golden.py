@@ -18,6 +18,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_kernels_7x6         all five kernels with max_degree 4 (15 monomials) and a field-dependent operator that
                           uses every term of the set incl. nodal_div_grad; field evaluators value / gradient / laplacian
   ref_config1_30x20       config 1 at full size: q, vals, coeffs, a row sample of B
+  ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
@@ -200,6 +201,30 @@ def case_mesh(tag):
     return out
 
 
+MULTI_CLOUD = dict(Nx=9, Ny=8, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+
+
+def case_multi(nb_iters=3):
+    """pde_multi_solver (operators.py:696-771) on two genuinely coupled equations,
+        lap(u0) - (1 + u1^2) u0 = 0,     lap(u1) + (x + u0) d(u1)/dx = -1."""
+    cloud = updes.SquareCloud(**MULTI_CLOUD)
+    rbf = partial(updes.polyharmonic, a=1)
+    zero, one = (lambda c: 0.0), (lambda c: 1.0)
+    bcs = [{"South": zero, "West": zero, "North": one, "East": zero}, {"South": zero, "West": one, "North": zero, "East": zero}]
+    op0 = lambda x, c, r, m, f: updes.nodal_laplacian(x, c, r, m) - (1.0 + f[1] ** 2) * updes.nodal_value(x, c, r, m)
+    op1 = lambda x, c, r, m, f: updes.nodal_laplacian(x, c, r, m) + (x[0] + f[0]) * updes.nodal_gradient(x, c, r, m)[0]
+    rhs0 = lambda x, centers, rbf, fields: 0.0
+    rhs1 = lambda x, centers, rbf, fields: -1.0
+    z = jnp.zeros((cloud.N,))
+    out = dict(cloud_arrays(cloud), nb_iters=np.array(nb_iters))
+    for k in range(1, nb_iters + 1):        # the state after every sweep (the reference returns only the last one)
+        sols = updes.pde_multi_solver([op0, op1], [rhs0, rhs1], cloud, bcs, rbf, 1, nb_iters=k, diff_args=[[z, z], [z, z]],
+                                      rhs_args=[None, None])
+        out["vals0_after_%d" % k], out["vals1_after_%d" % k] = npa(sols[0].vals), npa(sols[1].vals)
+    out["coeffs0"], out["coeffs1"] = npa(sols[0].coeffs), npa(sols[1].coeffs)
+    return out
+
+
 def case_config3(nb_iter=2):
     """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
     is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
@@ -222,7 +247,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_config3_ns_2iter": case_config3}
+         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi}
 
 
 def main():

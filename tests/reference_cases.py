@@ -152,3 +152,17 @@ def oracle_config3_loop(oracle, interpolate_field, bcs, cv, cp, nb_iter=2, Re=10
         ru, rv = ustar - gradphi[:, 0], vstar - gradphi[:, 1]
         out.append((ru, rv, rp_))
     return out
+
+
+MULTI_CLOUD = dict(Nx=9, Ny=8, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+
+
+def multi_problem(lib):
+    """The coupled pair of tests/golden/make_reference_golden.py:case_multi on the product's surface."""
+    zero, one = (lambda c: 0.0), (lambda c: 1.0)
+    bcs = [{"South": zero, "West": zero, "North": one, "East": zero}, {"South": zero, "West": one, "North": zero, "East": zero}]
+    op0 = lambda x, c, r, m, f: lib.nodal_laplacian(x, c, r, m) - (1.0 + f[1] ** 2) * lib.nodal_value(x, c, r, m)
+    op1 = lambda x, c, r, m, f: lib.nodal_laplacian(x, c, r, m) + (x[0] + f[0]) * lib.nodal_gradient(x, c, r, m)[0]
+    rhs0 = lambda x, centers, rbf, fields: 0.0
+    rhs1 = lambda x, centers, rbf, fields: -1.0
+    return [op0, op1], [rhs0, rhs1], bcs, partial(lib.polyharmonic, a=1)

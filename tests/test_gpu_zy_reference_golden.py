@@ -160,3 +160,18 @@ def test_config3_projection_loop_against_the_reference_demo():
             worst = max(worst, rel(got, want))
             print("iteration %d %s product-vs-reference-demo %.2e" % (it, nm, rel(got, want)))
     assert worst <= 2e-5, worst
+
+
+def test_pde_multi_solver_against_the_reference():
+    """pde_multi_solver (operators.py:696-771) on two genuinely coupled equations: the state after 1, 2 and 3 sweeps
+    against what the reference's own pde_multi_solver returned."""
+    g = rc.load("ref_multi_solver_9x8")
+    cloud = u.SquareCloud(**rc.MULTI_CLOUD)
+    rc.assert_cloud_equals_golden(cloud, g)
+    ops_, rhs_, bcs, rbf = rc.multi_problem(u)
+    z = np.zeros(cloud.N)
+    for k in range(1, int(g["nb_iters"]) + 1):
+        sols = u.pde_multi_solver(ops_, rhs_, cloud, bcs, rbf, 1, nb_iters=k, diff_args=[[z, z], [z, z]], rhs_args=[None, None])
+        for i in range(2):
+            want = g["vals%d_after_%d" % (i, k)]
+            assert np.max(np.abs(sols[i].vals - want)) <= 1e-8 * np.max(np.abs(want)), (k, i)

@@ -241,3 +241,28 @@ def test_oracle_config3_projection_loop_matches_the_reference_demo(oracle):
             print("iteration %d %s oracle-vs-reference-demo %.2e" % (it, nm, rel(got, want)))
     assert worst <= 2e-5, worst
     assert np.abs(g["u"][-1]).max() > 0.5           # a developed channel flow
+
+
+def test_oracle_picard_loop_matches_the_reference_multi_solver(oracle):
+    """pde_multi_solver of the reference (operators.py:696-771) on two genuinely coupled equations: every sweep solves
+    all equations with the PREVIOUS sweep's values.  Restated with explicit coefficient tables on the oracle."""
+    g = rc.load("ref_multi_solver_9x8")
+    cloud = oracle.RefSquareCloud(9, 8, rc.MULTI_CLOUD["facet_types"])
+    rc.assert_cloud_equals_golden(cloud, g)
+    Ni, xs = cloud.Ni, cloud.sorted_nodes[:cloud.Ni, 0]
+    north, west = np.asarray(cloud.facet_nodes["North"]), np.asarray(cloud.facet_nodes["West"])
+    bc = lambda ids: {f: (np.ones(len(v)) if v is ids else np.zeros(len(v))) for f, v in ((k, np.asarray(cloud.facet_nodes[k])) for k in cloud.facet_nodes)}
+    bc0 = {f: (np.ones(len(v)) if f == "North" else np.zeros(len(v))) for f, v in cloud.facet_nodes.items()}
+    bc1 = {f: (np.ones(len(v)) if f == "West" else np.zeros(len(v))) for f, v in cloud.facet_nodes.items()}
+    q0, q1 = oracle.assemble_q(cloud, np.zeros(Ni), bc0), oracle.assemble_q(cloud, -np.ones(Ni), bc1)
+    prev = [np.zeros(cloud.N), np.zeros(cloud.N)]
+    for k in range(1, int(g["nb_iters"]) + 1):
+        c0 = np.stack([-(1.0 + prev[1][:Ni] ** 2), np.zeros(Ni), np.zeros(Ni), np.ones(Ni), np.ones(Ni)], axis=1)
+        c1 = np.stack([np.zeros(Ni), xs + prev[0][:Ni], np.zeros(Ni), np.ones(Ni), np.ones(Ni)], axis=1)
+        v0, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 1, c0, q0)
+        v1, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 1, c1, q1)
+        prev = [v0, v1]
+        for i, v in enumerate(prev):
+            want = g["vals%d_after_%d" % (i, k)]
+            assert np.max(np.abs(v - want)) <= 1e-8 * np.max(np.abs(want)), (k, i)
+    assert np.max(np.abs(g["vals0_after_3"] - g["vals0_after_1"])) >= 1e-4 * np.max(np.abs(g["vals0_after_3"]))     # the coupling is real
