@@ -181,6 +181,11 @@ def case_kernels():
         out["%s_value" % name] = npa(updes.value_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
         out["%s_gradient" % name] = npa(updes.gradient_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
         out["%s_laplacian" % name] = npa(updes.laplacian_vec(jnp.array(pts), coeffs, cloud.sorted_nodes, rbf))
+        coeffs2 = jnp.array(rng.normal(size=cloud.N + 15))
+        out["%s_coeffs2" % name] = npa(coeffs2)
+        out["%s_divergence" % name] = npa(updes.divergence_vec(jnp.array(pts), jnp.stack([coeffs, coeffs2], axis=-1), cloud.sorted_nodes, rbf))
+        # coefficients of a nodal field: inv(A) [field; 0] (assembly.py:404-430), degree 2 keeps cond(A) moderate
+        out["%s_field_coeffs" % name] = npa(updes.get_field_coefficients(jnp.array(f1), cloud, rbf, 2))
     out["kernel_names"] = np.array([k[0] for k in KERNELS])
     out["kernel_params"] = np.array([float(k[2]) for k in KERNELS])
     return out

@@ -114,6 +114,10 @@ def test_all_kernels_degree4_and_field_evaluators():
         for what, got, want in (("value", v, g[name + "_value"]), ("gradient", gr, g[name + "_gradient"]), ("laplacian", lp, g[name + "_laplacian"])):
             err = np.max(np.abs(np.asarray(got) - want)) / np.max(np.abs(want))
             assert err <= 1e-10, (name, what, err)
+        div = u.divergence_vec(pts, np.stack([cf, g[name + "_coeffs2"]], axis=-1), cloud.sorted_nodes, rbf)
+        assert np.max(np.abs(div - g[name + "_divergence"])) <= 1e-10 * np.max(np.abs(g[name + "_divergence"])), name
+        fc = u.get_field_coefficients(g["f1"], cloud, rbf, 2)                    # cached LU of A instead of inv(A)
+        assert np.max(np.abs(fc - g[name + "_field_coeffs"])) <= 1e-8 * np.max(np.abs(g[name + "_field_coeffs"])), name
 
 
 def test_config1_full_size_against_the_reference_solution():

@@ -112,6 +112,12 @@ def test_oracle_all_kernels_degree4_and_field_evaluators(oracle):
                             ("laplacian", g[name + "_laplacian"])):
             got = oracle.eval_field(pts, cloud.sorted_nodes, cf, name, param, which)
             assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)), (name, which)
+        # divergence of the vector field (coeffs, coeffs2) (operators.py:294-312) and inv(A) [f1; 0] (assembly.py:404-430)
+        div = (oracle.eval_field(pts, cloud.sorted_nodes, cf, name, param, "dx")
+               + oracle.eval_field(pts, cloud.sorted_nodes, g[name + "_coeffs2"], name, param, "dy"))
+        assert np.max(np.abs(div - g[name + "_divergence"])) <= 1e-12 * np.max(np.abs(g[name + "_divergence"])), name
+        fc = np.linalg.solve(oracle.assemble_A(cloud, name, param, 6), np.concatenate([g["f1"], np.zeros(6)]))
+        assert np.max(np.abs(fc - g[name + "_field_coeffs"])) <= 1e-8 * np.max(np.abs(g[name + "_field_coeffs"])), name
 
 
 def test_oracle_config1_full_size_solution(oracle):
