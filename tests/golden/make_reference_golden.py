@@ -18,6 +18,8 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_kernels_7x6         all five kernels with max_degree 4 (15 monomials) and a field-dependent operator that
                           uses every term of the set incl. nodal_div_grad; field evaluators value / gradient / laplacian
   ref_config1_30x20       config 1 at full size: q, vals, coeffs, a row sample of B
+  ref_fuzz_16             16 random small problems: facet types incl. periodic pairs in random dict order, Robin + Neumann mixes,
+                          all kernels and degrees 0-4, fully general operator with five nodal fields: diffMat of each
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
@@ -206,6 +208,71 @@ def case_mesh(tag):
     return out
 
 
+FUZZ_KERNELS = [("polyharmonic", "a", [1, 2, 3]), ("thin_plate", "a", [1, 2]), ("gaussian", "eps", [0.7, 2.0, 5.0]),
+                ("multiquadric", "eps", [0.5, 1.0, 3.0]), ("inverse_multiquadric", "eps", [0.8, 2.5])]
+
+
+def fuzz_configs(seed=2024, ncases=16):
+    """Random small problems: grid size, facet types (d / n / r / periodic pairs) in a random DICT ORDER (the reference's
+    corner precedence, periodic-class suffixes and renumbering depend on it), kernel + parameter, polynomial degree."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(ncases):
+        nx, ny = int(rng.integers(5, 9)), int(rng.integers(5, 8))
+        pattern = k % 4
+        t = {f: str(rng.choice(["d", "n", "r"])) for f in ("South", "North", "West", "East")}
+        if pattern == 1:
+            t["South"] = t["North"] = "p1"
+        elif pattern == 2:
+            t["West"] = t["East"] = "p1"
+        elif pattern == 3:
+            a, b = ("p1", "p2") if rng.random() < 0.5 else ("p2", "p1")
+            t["South"] = t["North"] = a
+            t["West"] = t["East"] = b
+        order = [str(v) for v in rng.permutation(["South", "North", "West", "East"])]
+        name, pname, vals = FUZZ_KERNELS[int(rng.integers(len(FUZZ_KERNELS)))]
+        out.append(dict(Nx=nx, Ny=ny, facets={f: t[f] for f in order}, kernel=name, pname=pname,
+                        param=vals[int(rng.integers(len(vals)))], degree=int(rng.integers(0, 5)), seed=int(rng.integers(1 << 30))))
+    return out
+
+
+def case_fuzz():
+    """diffMat = [[opPhi opP], [bdPhi bdP]] of every random problem, with a fully general operator
+    f0 phi + f1 phi_x + f2 phi_y + f3 phi_xx + f4 phi_yy (five random nodal fields) and random Robin coefficients
+    given the way a user gives them: (value, beta array) tuples per Robin facet."""
+    def op(x, center, rbf, monomial, fields):
+        val = updes.nodal_value(x, center, rbf, monomial)
+        grad = updes.nodal_gradient(x, center, rbf, monomial)
+        dg = updes.nodal_div_grad(x, center, rbf, monomial, (fields[3], fields[4]))
+        return fields[0] * val + jnp.dot(jnp.array([fields[1], fields[2]]), grad) + dg
+
+    out = {}
+    cfgs = fuzz_configs()
+    for k, cfg in enumerate(cfgs):
+        rng = np.random.default_rng(cfg["seed"])
+        cloud = updes.SquareCloud(Nx=cfg["Nx"], Ny=cfg["Ny"], facet_types=dict(cfg["facets"]))
+        rbf = partial(getattr(updes, cfg["kernel"]), **{cfg["pname"]: cfg["param"]})
+        fields = rng.normal(size=(5, cloud.N))
+        bcs = {}
+        for f, ft in cloud.facet_types.items():
+            nf = len(cloud.facet_nodes[f])
+            bcs[f] = (jnp.zeros((nf,)), jnp.array(rng.uniform(0.2, 3.0, size=nf))) if ft == "r" else jnp.zeros((nf,))
+        robin, _ = updes.duplicate_robin_coeffs(bcs, cloud)
+        b = blocks(op, cloud, rbf, cfg["degree"], [jnp.array(f) for f in fields], robin)
+        pre = "c%02d_" % k
+        out[pre + "diffMat"] = np.concatenate([np.concatenate([b["opPhi"], b["opP"]], axis=1), np.concatenate([b["bdPhi"], b["bdP"]], axis=1)], axis=0)
+        out[pre + "fields"] = fields
+        out[pre + "betas"] = np.array([float(robin[i]) for i in sorted(robin)]) if robin else np.zeros(0)
+        ca = cloud_arrays(cloud)
+        for key in ("sorted_nodes", "sorted_outward_normals", "counts", "Np", "facet_names", "facet_sizes", "facet_nodes", "facet_types"):
+            out[pre + key] = ca[key]
+        out[pre + "config"] = np.array([cfg["Nx"], cfg["Ny"], cfg["degree"]])
+        out[pre + "kernel"] = np.array([cfg["kernel"], str(cfg["param"])])
+        out[pre + "facets_in"] = np.array([[f, t] for f, t in cfg["facets"].items()])
+    out["ncases"] = np.array(len(cfgs))
+    return out
+
+
 MULTI_CLOUD = dict(Nx=9, Ny=8, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
 
 
@@ -252,7 +319,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi}
+         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz}
 
 
 def main():

@@ -166,3 +166,21 @@ def multi_problem(lib):
     rhs0 = lambda x, centers, rbf, fields: 0.0
     rhs1 = lambda x, centers, rbf, fields: -1.0
     return [op0, op1], [rhs0, rhs1], bcs, partial(lib.polyharmonic, a=1)
+
+
+CLOUD_KEYS = ("sorted_nodes", "sorted_outward_normals", "counts", "Np", "facet_names", "facet_sizes", "facet_nodes", "facet_types")
+
+
+def fuzz_cases():
+    """(k, Nx, Ny, facet dict in the generator's order, kernel, param, M, fields (5, N), betas or None, golden sub-dict)
+    for every random problem of tests/golden/ref_fuzz_16.npz."""
+    g = load("ref_fuzz_16")
+    for k in range(int(g["ncases"])):
+        pre = "c%02d_" % k
+        nx, ny, deg = (int(v) for v in g[pre + "config"])
+        facets = {str(f): str(t) for f, t in g[pre + "facets_in"]}
+        sub = {key: g[pre + key] for key in CLOUD_KEYS}
+        sub["diffMat"] = g[pre + "diffMat"]
+        betas = g[pre + "betas"] if len(g[pre + "betas"]) else None
+        import math
+        yield k, nx, ny, facets, str(g[pre + "kernel"][0]), float(g[pre + "kernel"][1]), math.comb(deg + 2, deg), g[pre + "fields"], betas, sub

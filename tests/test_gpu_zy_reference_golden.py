@@ -179,3 +179,17 @@ def test_pde_multi_solver_against_the_reference():
         for i in range(2):
             want = g["vals%d_after_%d" % (i, k)]
             assert np.max(np.abs(sols[i].vals - want)) <= 1e-8 * np.max(np.abs(want)), (k, i)
+
+
+def test_random_problems_through_the_cuda_assembly():
+    """The 16 random problems of tests/golden/ref_fuzz_16.npz (facet mixes incl. periodic pairs in random dict order,
+    Neumann + Robin together, all kernels, degrees 0-4, general five-field operator): CUDA rows vs the reference's diffMat."""
+    for k, nx, ny, facets, kind, param, M, fields, betas, g in rc.fuzz_cases():
+        cloud = u.SquareCloud(Nx=nx, Ny=ny, facet_types=dict(facets))
+        rc.assert_cloud_equals_golden(cloud, g)
+        coef = fields[:, :cloud.Ni].T.copy()
+        K = _assemble(cloud, asm.build_operator_rows(cloud, coef, None, betas), kind, param, M)
+        got, want = K[:cloud.N], g["diffMat"]
+        e, t = rel_err_rowscaled(got, want), true_rel_err(got, want)
+        assert e <= 1e-12, (k, kind, param, e)
+        assert t <= 2e-10, (k, kind, param, t)

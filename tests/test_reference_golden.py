@@ -272,3 +272,26 @@ def test_oracle_picard_loop_matches_the_reference_multi_solver(oracle):
             want = g["vals%d_after_%d" % (i, k)]
             assert np.max(np.abs(v - want)) <= 1e-8 * np.max(np.abs(want)), (k, i)
     assert np.max(np.abs(g["vals0_after_3"] - g["vals0_after_1"])) >= 1e-4 * np.max(np.abs(g["vals0_after_3"]))     # the coupling is real
+
+
+def test_random_problems_oracle_and_product_host_match_the_reference(oracle):
+    """16 random small problems run through the reference (tests/golden/ref_fuzz_16.npz): facet types d / n / r /
+    periodic pairs in a random dict order (corner precedence, periodic-class suffixes and the renumbering depend on it),
+    Neumann + Robin + periodic mixes, every kernel, degrees 0-4, a fully general operator with five nodal fields."""
+    seen = set()
+    for k, nx, ny, facets, kind, param, M, fields, betas, g in rc.fuzz_cases():
+        ocloud = oracle.RefSquareCloud(nx, ny, dict(facets))
+        pcloud = u.SquareCloud(Nx=nx, Ny=ny, facet_types=dict(facets))
+        rc.assert_cloud_equals_golden(ocloud, g)
+        rc.assert_cloud_equals_golden(pcloud, g)
+        coef = fields[:, :ocloud.Ni].T.copy()
+        D = oracle.assemble_diffMat(ocloud, kind, param, M, coef, betas)
+        assert rel_err_rowscaled(D, g["diffMat"]) <= 1e-12 and true_rel_err(D, g["diffMat"]) <= 1e-10, k
+        # the product's symbolic lowering of the same operator gives exactly these coefficients
+        def op(x, center, rbf, monomial, f):
+            return (f[0] * u.nodal_value(x, center, rbf, monomial) + u.dot([f[1], f[2]], u.nodal_gradient(x, center, rbf, monomial))
+                    + u.nodal_div_grad(x, center, rbf, monomial, (f[3], f[4])))
+        cphi, cpol = u.lower_diff_operator(op, pcloud, rc.kernel_rbf(u, kind, param), list(fields))
+        assert np.array_equal(cphi, coef) and np.array_equal(cpol, coef), k
+        seen.add((pcloud.Nn > 0, pcloud.Nr > 0, len(pcloud.Np)))
+    assert {(True, True, 1), (False, False, 2), (False, True, 0)} <= seen          # Neumann + Robin + periodic; doubly periodic; Robin only
