@@ -20,6 +20,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_config1_30x20       config 1 at full size: q, vals, coeffs, a row sample of B
   ref_fuzz_16             16 random small problems: facet types incl. periodic pairs in random dict order, Robin + Neumann mixes,
                           all kernels and degrees 0-4, fully general operator with five nodal fields: diffMat of each
+  ref_generated_msh       GmshCloud on two channel meshes written by tests/golden/make_msh.py, two facet-type orders
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
@@ -208,6 +209,28 @@ def case_mesh(tag):
     return out
 
 
+GENERATED_MSH = [("a", {"Wall": "d", "Inflow": "n", "Outflow": "r"}, 13, 9), ("b", {"Outflow": "n", "Wall": "r", "Inflow": "d"}, 10, 12)]
+
+
+def case_generated_msh():
+    """The reference's GmshCloud on Gmsh-4.0 meshes written by tests/golden/make_msh.py (own data, regenerated by the
+    tests): corner-to-facet assignment by facet_types ORDER (cloud.py:39-40, :680-688) and the computed normals."""
+    import tempfile
+    sys.path.insert(0, HERE)
+    from make_msh import write_channel_msh
+    out = {}
+    for tag, ft, nx, ny in GENERATED_MSH:
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "channel.msh")
+            write_channel_msh(path, nx=nx, ny=ny)
+            cloud = updes.GmshCloud(filename=path, facet_types=dict(ft))
+        for k, v in cloud_arrays(cloud).items():
+            out["%s_%s" % (tag, k)] = v
+        out["%s_facets_in" % tag] = np.array([[f, t] for f, t in ft.items()])
+        out["%s_grid" % tag] = np.array([nx, ny])
+    return out
+
+
 FUZZ_KERNELS = [("polyharmonic", "a", [1, 2, 3]), ("thin_plate", "a", [1, 2]), ("gaussian", "eps", [0.7, 2.0, 5.0]),
                 ("multiquadric", "eps", [0.5, 1.0, 3.0]), ("inverse_multiquadric", "eps", [0.8, 2.5])]
 
@@ -319,7 +342,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz}
+         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
 
 
 def main():

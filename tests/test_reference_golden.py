@@ -295,3 +295,21 @@ def test_random_problems_oracle_and_product_host_match_the_reference(oracle):
         assert np.array_equal(cphi, coef) and np.array_equal(cpol, coef), k
         seen.add((pcloud.Nn > 0, pcloud.Nr > 0, len(pcloud.Np)))
     assert {(True, True, 1), (False, False, 2), (False, True, 0)} <= seen          # Neumann + Robin + periodic; doubly periodic; Robin only
+
+
+def test_gmsh_readers_match_the_reference_on_generated_meshes(tmp_path, oracle):
+    """Gmsh-4.0 channel meshes written by tests/golden/make_msh.py (regenerated here): the product's reader and the
+    oracle's restatement against what the reference's GmshCloud made of the same files -- corner nodes go to the facet
+    that comes first in the facet_types dict, normals point away from the nearest internal node."""
+    from golden.make_msh import write_channel_msh
+    g = rc.load("ref_generated_msh")
+    for tag in ("a", "b"):
+        nx, ny = (int(v) for v in g[tag + "_grid"])
+        facets = {str(f): str(t) for f, t in g[tag + "_facets_in"]}
+        path = str(tmp_path / ("channel_%s.msh" % tag))
+        write_channel_msh(path, nx=nx, ny=ny)
+        sub = {k: g["%s_%s" % (tag, k)] for k in rc.CLOUD_KEYS}
+        for cloud in (u.GmshCloud(path, facet_types=dict(facets)), oracle.RefGmshCloud(path, dict(facets))):
+            rc.assert_cloud_equals_golden(cloud, sub)
+            old_of_new = [o for o, _ in sorted(cloud.renumbering_map.items(), key=lambda kv: kv[1])]
+            assert old_of_new == g[tag + "_old_of_new"].tolist()
