@@ -438,3 +438,50 @@ def test_distributed_layout_selection(monkeypatch):
     finally:
         ops.disable_distributed()
     assert ops._DIST == {"enabled": False, "group": None, "grid": None}
+
+
+def test_numeric_probe_lowering_of_operators_that_leave_the_symbolic_world():
+    """An operator whose body needs numbers (float(), np.asarray, a foreign array library) cannot be traced symbolically;
+    lower_diff_operator then probes it numerically row by row: unit jets in, coefficients out, linearity checked."""
+    cloud = u.SquareCloud(Nx=8, Ny=6, facet_types=CONFIG1_FACETS)
+    Ni = cloud.Ni
+    f0, f1 = np.linspace(1, 2, cloud.N), np.linspace(-1, 1, cloud.N)
+
+    def op(x, center, rbf, monomial, fields):
+        g = np.asarray(u.nodal_gradient(x, center, rbf, monomial), dtype=float)        # forces numbers
+        lap = float(u.nodal_laplacian(x, center, rbf, monomial))
+        dg = u.nodal_div_grad(x, center, rbf, monomial, (fields[0], 2.0))
+        return float(fields[1]) * float(u.nodal_value(x, center, rbf, monomial)) + float(np.dot([x[0], -0.5], g)) - 0.25 * lap + dg
+
+    cphi, cpol = u.lower_diff_operator(op, cloud, u.polyharmonic, [f0, f1])
+    xs = cloud.sorted_nodes[:Ni, 0]
+    want = np.stack([f1[:Ni], xs, np.full(Ni, -0.5), f0[:Ni] - 0.25, np.full(Ni, 2.0 - 0.25)], axis=1)
+    assert np.allclose(cphi, want, rtol=1e-15, atol=0) and np.array_equal(cphi, cpol)
+    # the same machinery rejects what the symbolic path rejects
+    for bad in (lambda x, c, r, m, f: float(u.nodal_value(x, c, r, m)) ** 2,
+                lambda x, c, r, m, f: float(u.nodal_value(x, c, r, m)) + 1.0,
+                lambda x, c, r, m, f: float(u.nodal_value(x, c, r, m)) * float(u.nodal_laplacian(x, c, r, m))):
+        with pytest.raises(u.OperatorLoweringError):
+            u.lower_diff_operator(bad, cloud, u.polyharmonic)
+    # and the term set is still unavailable outside an operator
+    with pytest.raises(u.OperatorLoweringError):
+        u.nodal_value(np.zeros(2), np.zeros(2), u.polyharmonic, None)
+
+
+def test_numeric_probe_batch_result_is_validated_against_per_node_evaluation():
+    """A body that forces numbers and reduces over 'all axes' means one node's two gradient components in the
+    reference's vmap semantics, but would sum over every row on batched arrays: the batched table is discarded."""
+    cloud = u.SquareCloud(Nx=7, Ny=6, facet_types=CONFIG1_FACETS)
+    op = lambda x, c, r, m, f: np.sum(np.asarray(u.nodal_gradient(x, c, r, m), dtype=float)) + 0.0 * np.sum(x)
+    cphi, _ = u.lower_diff_operator(op, cloud, u.polyharmonic)
+    assert np.array_equal(cphi, np.tile([0.0, 1.0, 1.0, 0.0, 0.0], (cloud.Ni, 1)))
+
+
+def test_batched_symbolic_lowering_is_validated_against_per_node_evaluation():
+    """np.sum(x) is x + y of ONE node in the reference's semantics; on the batched (2, Ni) coordinates it would silently
+    become the sum over all rows.  Sample rows are re-evaluated per node and the batched table is discarded."""
+    cloud = u.SquareCloud(Nx=7, Ny=6, facet_types=CONFIG1_FACETS)
+    op = lambda x, c, r, m, f: np.sum(x) * u.nodal_value(x, c, r, m) + u.nodal_laplacian(x, c, r, m)
+    cphi, cpol = u.lower_diff_operator(op, cloud, u.polyharmonic)
+    xy = cloud.sorted_nodes[:cloud.Ni]
+    assert np.allclose(cphi[:, 0], xy[:, 0] + xy[:, 1], rtol=1e-15, atol=0) and np.all(cphi[:, 3:] == 1.0) and np.array_equal(cphi, cpol)

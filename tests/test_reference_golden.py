@@ -313,3 +313,12 @@ def test_gmsh_readers_match_the_reference_on_generated_meshes(tmp_path, oracle):
             rc.assert_cloud_equals_golden(cloud, sub)
             old_of_new = [o for o, _ in sorted(cloud.renumbering_map.items(), key=lambda kv: kv[1])]
             assert old_of_new == g[tag + "_old_of_new"].tolist()
+
+
+def test_reference_style_operators_with_a_foreign_array_library_lower_through_numeric_probes():
+    """Operators as the reference's demos write them hand the nodal terms to jnp (`jnp.dot(U_prev, nodal_gradient(...))`):
+    symbolic lowering cannot follow that, the numeric-probe fallback can -- and still rejects non-linear / affine bodies.
+    Runs in a subprocess because it puts the JAX stand-in on sys.path; with /root/reference mounted the operator source is
+    the demo's own text (demos/NavierStokes/30_channel_flow_blowing_suction.py:61-65)."""
+    r = _run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "lowering_with_foreign_arrays.py")], ROOT, 600)
+    assert r.returncode == 0 and "OK bc + rhs" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -30,6 +30,11 @@ class OperatorLoweringError(TypeError):
     """The user's differential operator is outside the supported (linear, built-in term) set."""
 
 
+class _SymbolicEscape(OperatorLoweringError):
+    """A symbolic nodal term reached code that needs numbers (``jnp.dot``, ``np.asarray``, ``float`` ...).  The operator
+    may still be linear: ``lower_diff_operator`` retries it with numeric probes before giving up."""
+
+
 # ==================================================================================================
 # Symbolic jets
 # ==================================================================================================
@@ -84,10 +89,10 @@ class Jet:
         raise OperatorLoweringError("powers of a nodal term are non-linear in the basis function")
 
     def __float__(self):
-        raise OperatorLoweringError("nodal terms are symbolic during assembly and have no numeric value")
+        raise _SymbolicEscape("nodal terms are symbolic during assembly and have no numeric value")
 
     def __array__(self, *a, **k):
-        raise OperatorLoweringError(
+        raise _SymbolicEscape(
             "a nodal term was passed to a numpy function; only + - * / with coefficients, indexing of "
             "nodal_gradient and dot products are supported")
 
@@ -142,7 +147,7 @@ class JetVector:
             for c in self.comps[1:]:
                 out = out + c
             return out
-        raise OperatorLoweringError("numpy function %s is not supported on a nodal gradient" % getattr(func, "__name__", func))
+        raise _SymbolicEscape("numpy function %s is not supported on a nodal gradient" % getattr(func, "__name__", func))
 
 
 def dot(a, b):
@@ -166,6 +171,30 @@ _CENTER = _Basis("rbf centre")
 _MONOMIAL = _Basis("monomial")
 
 
+class _Probe:
+    """Numeric stand-in for 'the basis function': its jet (phi, phi_x, phi_y, phi_xx, phi_yy) at the evaluation point is
+    a fixed vector.  An operator that is linear in the term set maps the five unit jets to its five coefficients, whatever
+    numeric library its body uses (``jnp.dot``, ``jnp.array([...])``, torch ...): the fallback of ``lower_diff_operator``
+    for operators written against the reference (updes/operators.py:15-111 differentiates a real kernel there)."""
+
+    def __init__(self, name, jet):
+        self.name, self.jet = name, jet
+
+    def __repr__(self):
+        return "<numeric probe of the %s>" % self.name
+
+    def __call__(self, *a, **k):
+        raise OperatorLoweringError("the %s cannot be called during assembly; use the nodal_* term set" % self.name)
+
+
+def _probe_of(center, monomial):
+    if isinstance(center, _Probe):
+        return center
+    if isinstance(monomial, _Probe):
+        return monomial
+    return None
+
+
 def _check_symbolic(center, monomial, what):
     if center is _CENTER or monomial is _MONOMIAL:
         return
@@ -176,27 +205,39 @@ def _check_symbolic(center, monomial, what):
 
 def nodal_value(x, center=None, rbf=None, monomial=None):
     """rbf or monomial value at x (operators.py:15-32)."""
+    p = _probe_of(center, monomial)
+    if p is not None:
+        return p.jet[0]
     _check_symbolic(center, monomial, "nodal_value")
     return Jet([1.0, 0.0, 0.0, 0.0, 0.0])
 
 
 def nodal_gradient(x, center=None, rbf=None, monomial=None):
     """gradient w.r.t. x, NaN/inf at r = 0 replaced by 0 (operators.py:42-60)."""
+    p = _probe_of(center, monomial)
+    if p is not None:
+        return np.array([p.jet[1], p.jet[2]])
     _check_symbolic(center, monomial, "nodal_gradient")
     return JetVector([Jet([0.0, 1.0, 0.0, 0.0, 0.0]), Jet([0.0, 0.0, 1.0, 0.0, 0.0])])
 
 
 def nodal_laplacian(x, center=None, rbf=None, monomial=None):
     """trace of the Hessian w.r.t. x (operators.py:70-85)."""
+    p = _probe_of(center, monomial)
+    if p is not None:
+        return p.jet[3] + p.jet[4]
     _check_symbolic(center, monomial, "nodal_laplacian")
     return Jet([0.0, 0.0, 0.0, 1.0, 1.0])
 
 
 def nodal_div_grad(x, center=None, rbf=None, monomial=None, args=None):
     """args[0] phi_xx + args[1] phi_yy (operators.py:88-111)."""
-    _check_symbolic(center, monomial, "nodal_div_grad")
     if args is None or len(args) != 2:
         raise OperatorLoweringError("nodal_div_grad needs args=(a, b)")
+    p = _probe_of(center, monomial)
+    if p is not None:
+        return args[0] * p.jet[3] + args[1] * p.jet[4]
+    _check_symbolic(center, monomial, "nodal_div_grad")
     return Jet([0.0, 0.0, 0.0, args[0], args[1]])
 
 
@@ -268,8 +309,10 @@ def lower_diff_operator(diff_operator, cloud, rbf, diff_args=None):
     for one node at a time -- a Python ``if`` on a coordinate, ``float(x[0])``, shape-dependent code:
     the reference vmaps the operator over nodes, so ``x`` is a (2,) point there (assembly.py:126-130) --
     make that call raise; the operator is then evaluated row by row with exactly the reference's
-    per-node arguments (``x`` (2,), ``fields[i]`` (nf,)).  Genuinely unsupported operators raise
-    ``OperatorLoweringError`` from both paths."""
+    per-node arguments (``x`` (2,), ``fields[i]`` (nf,)).  Operators whose body hands the nodal terms to a numeric
+    library (``jnp.dot(U, nodal_gradient(...))`` as in the reference's demos) cannot be traced symbolically; they are
+    evaluated row by row with NUMERIC probes instead (unit jets in, coefficients out, linearity checked per row).
+    Genuinely unsupported operators raise ``OperatorLoweringError`` from every path."""
     Ni, N = cloud.Ni, cloud.N
     F = _fields_table(diff_args, N, Ni)
     x = BatchPoints(cloud.sorted_nodes[:Ni].T)
@@ -279,22 +322,120 @@ def lower_diff_operator(diff_operator, cloud, rbf, diff_args=None):
         with _batch_rows(Ni):
             return _coef_table(diff_operator(x, center, rbf, monomial, fields), Ni)
 
+    def symbolic_row(i, center, monomial):
+        out = diff_operator(np.array(cloud.sorted_nodes[i]), center, rbf, monomial, np.ones(1) if F is None else F[i])
+        return _coef_table(out, 1)[0]
+
     def run_rows(center, monomial):
         tab = np.empty((Ni, 5))
-        ones = np.ones(1)
         for i in range(Ni):
-            out = diff_operator(np.array(cloud.sorted_nodes[i]), center, rbf, monomial, ones if F is None else F[i])
-            tab[i] = _coef_table(out, 1)[0]
+            tab[i] = symbolic_row(i, center, monomial)
         return tab
 
-    tabs = []
-    for center, monomial in ((_CENTER, None), (None, _MONOMIAL)):
+    def batch_agrees_with_rows(tab, center, monomial):
+        """The batched call is an optimisation of the reference's one-node-per-call semantics (assembly.py:126-130).  A body
+        written for one node can run on batched arrays and mean something else (a reduction over 'all' axes of x, say):
+        sample rows are re-evaluated node by node, and a batched table that does not reproduce them is discarded."""
+        for i in sorted({0, Ni // 3, Ni // 2, Ni - 1}):
+            try:
+                row = symbolic_row(i, center, monomial)
+            except Exception:
+                return True            # only the batched form runs: nothing to compare with
+            if not np.allclose(tab[i], row, rtol=1e-12, atol=1e-300):
+                return False
+        return True
+
+    def run_numeric(family):
+        """Numeric probes: the operator sees plain numbers, so its body may use any array library.  The zero jet must
+        give 0 (no affine part), the five unit jets give the coefficients, and one mixed jet must give the same mixture
+        (linearity).  First all rows at once (jets as (Ni,) vectors beside the batched x), then -- if the body only
+        makes sense for one node, the reference's vmap semantics -- one node per call."""
+        mix = (0.7, -1.3, 0.45, 1.9, -0.6)
+        jets = [(0.0,) * 5] + [tuple(float(j == k) for j in range(5)) for k in range(5)] + [mix]
+        name = "rbf centre" if family == 0 else "monomial"
+
+        def check(vals, where):
+            """vals: (7, R) outputs for the seven jets -> (R, 5) coefficients"""
+            if np.any(vals[0] != 0.0):
+                raise OperatorLoweringError(
+                    "the differential operator returns %g for a vanishing basis function%s: it has an affine part or does "
+                    "not involve the basis function (affine parts belong in the rhs operator)" % (vals[0].flat[np.argmax(vals[0] != 0)], where))
+            tab = vals[1:6].T.copy()
+            want = tab @ np.asarray(mix)
+            tol = 1e-9 * np.maximum(1.0, np.maximum(np.abs(want), np.max(np.abs(tab), axis=1)))
+            if not np.all(np.abs(vals[6] - want) <= tol):
+                raise OperatorLoweringError(
+                    "the differential operator is not linear in nodal_value / nodal_gradient / nodal_laplacian / "
+                    "nodal_div_grad%s (a mixed probe does not give the mixture of the unit probes)" % where)
+            return tab
+
+        def evaluate(xarg, farg, jet, rows):
+            pr = _Probe(name, jet)
+            out = diff_operator(xarg, pr if family == 0 else None, rbf, None if family == 0 else pr, farg)
+            out = np.asarray(out, dtype=np.float64)
+            if rows == 1 and out.size != 1:
+                raise OperatorLoweringError("the differential operator must return a scalar per node, got shape %s" % (out.shape,))
+            return np.broadcast_to(out.reshape(-1) if out.ndim else out, (rows,))
+
+        ones = np.ones(1)
+
+        def one_row(i):
+            xi, fi = np.array(cloud.sorted_nodes[i]), (ones if F is None else F[i])
+            return check(np.stack([evaluate(xi, fi, jet, 1) for jet in jets]), " at node %d" % i)[0]
+
         try:
-            tab = run_batch(center, monomial)
+            with _batch_rows(Ni):
+                vals = np.stack([evaluate(x, fields, tuple(np.full(Ni, v) for v in jet), Ni) for jet in jets])
+            tab = check(vals, "")
+            # a body written for ONE node can run on the batched arrays and mean something else (jnp.sum over both
+            # axes, say): the batched table is only kept if it reproduces per-node evaluation on sample rows
+            for i in sorted({0, Ni // 3, Ni // 2, Ni - 1}):
+                if not np.array_equal(tab[i], one_row(i)) and not np.allclose(tab[i], one_row(i), rtol=1e-14, atol=0):
+                    raise ValueError("batched evaluation differs from per-node evaluation")
+            return tab
         except OperatorLoweringError:
             raise
         except Exception:
-            tab = run_rows(center, monomial)      # reference semantics: one node per call
+            pass
+        tab = np.empty((Ni, 5))
+        for i in range(Ni):
+            tab[i] = one_row(i)
+        return tab
+
+    tabs = []
+    for family, (center, monomial) in enumerate(((_CENTER, None), (None, _MONOMIAL))):
+        try:
+            try:
+                tab = run_batch(center, monomial)
+                if Ni > 0 and not batch_agrees_with_rows(tab, center, monomial):
+                    tab = run_rows(center, monomial)
+            except _SymbolicEscape:
+                raise
+            except OperatorLoweringError:
+                raise
+            except Exception:
+                tab = run_rows(center, monomial)      # reference semantics: one node per call
+        except _SymbolicEscape as escape:
+            # a symbolic term reached numeric code (jnp.dot, np.asarray, float ...): ask the operator with numbers
+            try:
+                tab = run_numeric(family)
+            except OperatorLoweringError:
+                raise
+            except Exception as e:
+                raise OperatorLoweringError("the differential operator could not be evaluated numerically either (%s: %s); "
+                                            "symbolic lowering had failed with: %s" % (type(e).__name__, e, escape)) from e
+        except OperatorLoweringError:
+            raise
+        except Exception as first:
+            # neither batched nor per-node symbolic evaluation ran (e.g. a foreign array library rejected the symbolic
+            # terms with its own exception type): numeric probes, then give up with the explicit error
+            try:
+                tab = run_numeric(family)
+            except OperatorLoweringError:
+                raise
+            except Exception as e:
+                raise OperatorLoweringError("the differential operator could not be lowered: symbolic evaluation raised %s: %s; "
+                                            "numeric probing raised %s: %s" % (type(first).__name__, first, type(e).__name__, e)) from e
         if not np.all(np.isfinite(tab)):
             raise OperatorLoweringError("operator coefficients are not finite")
         tabs.append(tab)
