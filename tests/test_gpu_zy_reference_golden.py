@@ -193,3 +193,34 @@ def test_random_problems_through_the_cuda_assembly():
         e, t = rel_err_rowscaled(got, want), true_rel_err(got, want)
         assert e <= 1e-12, (k, kind, param, e)
         assert t <= 2e-10, (k, kind, param, t)
+
+
+def test_explicit_assembly_functions_against_the_reference():
+    """assemble_Phi / assemble_P / assemble_A / assemble_invert_A / assemble_op_Phi_P / assemble_bd_Phi_P / assemble_B under
+    the reference's names and signatures (updes/assembly.py:10-401), against what the reference's functions returned."""
+    g = rc.load("ref_laplace_12x9")
+    case = rc.laplace(u, 12, 9)
+    cloud = u.SquareCloud(**case.cloud_args)
+    N, M = cloud.N, 3
+    A = u.assemble_A(cloud, case.rbf, M)
+    assert A.shape == (N + M, N + M) and rel_err_rowscaled(A, g["A"]) <= 1e-12
+    assert rel_err_rowscaled(u.assemble_Phi(cloud, case.rbf), g["A"][:N, :N]) <= 1e-12
+    assert np.array_equal(u.assemble_P(cloud, M), g["A"][:N, N:])
+    opPhi, opP = u.assemble_op_Phi_P(case.op, cloud, case.rbf, M, None)
+    assert opPhi.shape == g["opPhi"].shape and rel_err_rowscaled(opPhi, g["opPhi"]) <= 1e-12 and rel_err_rowscaled(opP, g["opP"]) <= 1e-12
+    bdPhi, bdP = u.assemble_bd_Phi_P(cloud, case.rbf, M, {})
+    assert bdPhi.shape == g["bdPhi"].shape and rel_err_rowscaled(bdPhi, g["bdPhi"]) <= 1e-12 and rel_err_rowscaled(bdP, g["bdP"]) <= 1e-12
+    inv = u.assemble_invert_A(cloud, case.rbf, M)
+    want = np.linalg.inv(g["A"])
+    assert np.max(np.abs(inv - want)) <= 1e-8 * np.max(np.abs(want))              # cond(A) = 3e5
+    B = u.assemble_B(case.op, cloud, case.rbf, M, None, {})
+    assert np.max(np.abs(B - g["B"])) <= 1e-6 * np.max(np.abs(g["B"]))
+    # Robin + Neumann facets: coefficients given as the {node: beta} dict duplicate_robin_coeffs returns
+    g = rc.load("ref_robin_11x8")
+    case = rc.robin(u)
+    cloud = u.SquareCloud(**case.cloud_args)
+    robin, _ = u.duplicate_robin_coeffs(dict(u.boundary_conditions_func_to_arr(case.bcs, cloud)), cloud)
+    bdPhi, bdP = u.assemble_bd_Phi_P(cloud, case.rbf, 6, robin)
+    assert rel_err_rowscaled(bdPhi, g["bdPhi"]) <= 1e-12 and rel_err_rowscaled(bdP, g["bdP"]) <= 1e-12
+    opPhi, opP = u.assemble_op_Phi_P(case.op, cloud, case.rbf, 6, None)
+    assert rel_err_rowscaled(opPhi, g["opPhi"]) <= 1e-12 and rel_err_rowscaled(opP, g["opP"]) <= 1e-12

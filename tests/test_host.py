@@ -485,3 +485,25 @@ def test_batched_symbolic_lowering_is_validated_against_per_node_evaluation():
     cphi, cpol = u.lower_diff_operator(op, cloud, u.polyharmonic)
     xy = cloud.sorted_nodes[:cloud.Ni]
     assert np.allclose(cphi[:, 0], xy[:, 0] + xy[:, 1], rtol=1e-15, atol=0) and np.all(cphi[:, 3:] == 1.0) and np.array_equal(cphi, cpol)
+
+
+def test_explicit_assembly_names_exist_and_refuse_large_clouds():
+    """The reference's assemble_* names are exported (updes/assembly.py:10-401); explicit host matrices are refused
+    beyond N = 20 000 before anything touches the GPU."""
+    for name in ("assemble_Phi", "assemble_P", "assemble_A", "assemble_invert_A", "assemble_op_Phi_P", "assemble_bd_Phi_P",
+                 "assemble_B", "assemble_q", "core_compute_coefficients", "compute_coefficients", "get_field_coefficients"):
+        assert callable(getattr(u, name)), name
+
+    class Big:
+        N = 20001
+    for fn, args in ((u.assemble_A, (Big, u.polyharmonic, 3)), (u.assemble_invert_A, (Big, u.polyharmonic, 3)),
+                     (u.assemble_bd_Phi_P, (Big, u.polyharmonic, 3)), (u.assemble_B, (None, Big, u.polyharmonic, 3, None, {}))):
+        with pytest.raises(MemoryError):
+            fn(*args)
+    from updes_b200.explicit import _betas
+    cloud = u.SquareCloud(Nx=6, Ny=5, facet_types={"South": "r", "West": "d", "North": "d", "East": "n"})
+    ids = cloud.facet_nodes["South"]
+    assert np.array_equal(_betas(cloud, {i: 1.0 + k for k, i in enumerate(reversed(ids))}), np.arange(len(ids), 0, -1.0))
+    assert np.array_equal(_betas(cloud, None), np.zeros(cloud.Nr))
+    with pytest.raises(ValueError):
+        _betas(cloud, {ids[0]: 1.0})

@@ -17,5 +17,7 @@ from .operators import (BatchPoints, OperatorLoweringError, SteadySol, assemble_
                         zerofy_periodic_cond)
 
 from .autodiff import linear_solve
+from .explicit import (assemble_A, assemble_B, assemble_P, assemble_Phi, assemble_bd_Phi_P, assemble_invert_A,
+                       assemble_op_Phi_P)
 
 __version__ = "0.1.0"
