@@ -11,7 +11,8 @@ from .rbf import (compute_nb_monomials, distance, gaussian, identify_rbf, invers
 from .operators import (BatchPoints, OperatorLoweringError, SteadySol, assemble_q, boundary_conditions_func_to_arr, clear_cache,
                         disable_distributed, enable_distributed, interpolate_field,
                         compute_coefficients, core_compute_coefficients, divergence, divergence_vec, dot,
-                        duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vec, laplacian,
+                        duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vals, gradient_vals_vec, gradient_vec,
+                        laplacian, laplacian_vals, laplacian_vals_vec,
                         laplacian_vec, lower_diff_operator, nodal_div_grad, nodal_gradient, nodal_laplacian,
                         nodal_value, pde_multi_solver, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
                         zerofy_periodic_cond)

@@ -510,8 +510,8 @@ def divergence(x, field, centers, rbf=None, clip_val=None):
     return _clip(float(v[0]) if layout == "single" else v, clip_val)
 
 
-value_vec = value
-gradient_vec = gradient
+value_vec = value_vec_ = value                     # operators.py:149-150 (the evaluators take one point or many)
+gradient_vec = gradient_vec_ = gradient            # operators.py:183-184
 laplacian_vec = laplacian
 divergence_vec = divergence
 
@@ -929,6 +929,21 @@ def compute_coefficients(field, cloud, rbf, max_degree):
 
 
 get_field_coefficients = compute_coefficients      # assembly.py:423-430
+
+
+def gradient_vals(x, field, cloud, rbf, max_degree):
+    """Gradient at x of a field given by its nodal VALUES (operators.py:186-205): coefficients through the cached LU of
+    A, then the matrix-free evaluator.  ``x``: one point (2,) or points (R, 2)."""
+    return gradient(x, compute_coefficients(field, cloud, rbf, max_degree), cloud.sorted_nodes, rbf)
+
+
+def laplacian_vals(x, field, cloud, rbf, max_degree):
+    """Laplacian at x of a field given by its nodal values (operators.py:354-368)."""
+    return laplacian(x, compute_coefficients(field, cloud, rbf, max_degree), cloud.sorted_nodes, rbf)
+
+
+gradient_vals_vec = gradient_vals_vec_ = gradient_vals          # operators.py:207-208
+laplacian_vals_vec = laplacian_vals_vec_ = laplacian_vals       # operators.py:370-371
 
 
 def assemble_q(rhs_operator, boundary_conditions, cloud, rbf, nb_monomials, rhs_args):
