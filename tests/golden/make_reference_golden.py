@@ -22,6 +22,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
                           all kernels and degrees 0-4, fully general operator with five nodal fields: diffMat of each
   ref_generated_msh       GmshCloud on two channel meshes written by tests/golden/make_msh.py, two facet-type orders
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
+  ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
@@ -320,6 +321,28 @@ def case_multi(nb_iters=3):
     return out
 
 
+def case_config2(nb_steps=3):
+    """Config 2 as the reference's demo defines it: constants, cloud (35x35, doubly periodic, key = None), operators and
+    initial field are the source text of demos/Advection/01_adv_diff_periodic.py:34-93 executed unchanged; the time loop
+    below is the demo's own pde_solver_jit call (:106-113), run for three of its hundred steps."""
+    import jax
+    src = open(os.path.join(REFERENCE, "demos/Advection/01_adv_diff_periodic.py")).read()
+    body = src[src.index("RBF = partial(polyharmonic, a=1)"):src.index("## Begin timestepping for 100 steps")]
+    ns = {k: getattr(updes, k) for k in dir(updes) if not k.startswith("_")}
+    ns.update(jax=jax, jnp=jnp, partial=partial, key=None)
+    exec(compile(body, "01_adv_diff_periodic.py", "exec"), ns)
+    cloud, u = ns["cloud"], ns["u0"]
+    ulist = [npa(u)]
+    for _ in range(nb_steps):
+        ufield = updes.pde_solver_jit(diff_operator=ns["my_diff_operator"], rhs_operator=ns["my_rhs_operator"], rhs_args=[u],
+                                      cloud=cloud, boundary_conditions=ns["boundary_conditions"], rbf=ns["RBF"],
+                                      max_degree=ns["MAX_DEGREE"])
+        u = ufield.vals
+        ulist.append(npa(u))
+    return dict(cloud_arrays(cloud), u=np.stack(ulist), DT=np.array(ns["DT"]), K=np.array(ns["K"]), VEL=npa(ns["VEL"]),
+                max_degree=np.array(ns["MAX_DEGREE"]), coeffs_last=npa(ufield.coeffs))
+
+
 def case_config3(nb_iter=2):
     """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
     is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
@@ -342,7 +365,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
+         "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
 
 
 def main():

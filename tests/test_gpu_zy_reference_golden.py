@@ -3,6 +3,8 @@ tests/golden/make_reference_golden.py and oracle/refshim/README.md): the CUDA as
 whole pde_solver path, through the public API and the C-ABI, on the same problems the reference solved.
 Tolerances are the north_star's: matrix entries 1e-12 relative (row-scale floor; true per-entry error reported and
 bounded too), solutions 1e-8 relative or the cond-scaled backward-error clause."""
+from functools import partial
+
 import numpy as np
 import pytest
 
@@ -224,3 +226,37 @@ def test_explicit_assembly_functions_against_the_reference():
     assert rel_err_rowscaled(bdPhi, g["bdPhi"]) <= 1e-12 and rel_err_rowscaled(bdP, g["bdP"]) <= 1e-12
     opPhi, opP = u.assemble_op_Phi_P(case.op, cloud, case.rbf, 6, None)
     assert rel_err_rowscaled(opPhi, g["opPhi"]) <= 1e-12 and rel_err_rowscaled(opP, g["opP"]) <= 1e-12
+
+
+def test_config2_time_steps_against_the_reference_advection_demo():
+    """Config 2 as the reference's demo defines it (35x35 doubly periodic cloud, key = None): every step is taken from the
+    REFERENCE's previous field and compared with the reference's next field (north_star: 1e-8 relative); the factorisation
+    is reused after the first step."""
+    from updes_b200 import _lib
+    g = rc.load("ref_config2_advdiff_3steps")
+    facets = {"South": "p1", "North": "p1", "West": "p2", "East": "p2"}
+    cloud = u.SquareCloud(Nx=35, Ny=35, facet_types=facets)
+    rc.assert_cloud_equals_golden(cloud, g)
+    DT, K, VEL = float(g["DT"]), float(g["K"]), g["VEL"]
+
+    def op(x, center=None, rbf=None, monomial=None, fields=None):
+        val = u.nodal_value(x, center, rbf, monomial)
+        grad = u.nodal_gradient(x, center, rbf, monomial)
+        lap = u.nodal_laplacian(x, center, rbf, monomial)
+        return (val / DT) + u.dot(VEL, grad) - K * lap
+
+    rhs = lambda x, centers=None, rbf=None, fields=None: u.value(x, fields[:, 0], centers, rbf) / DT
+    bcs = {k: (lambda p: 0.0) for k in facets}
+    rbf = partial(u.polyharmonic, a=1)
+    u.clear_cache()
+    for s in range(g["u"].shape[0] - 1):
+        _lib.profile_enable(True)
+        sol = u.pde_solver_jit(diff_operator=op, rhs_operator=rhs, rhs_args=[g["u"][s]], cloud=cloud, boundary_conditions=bcs,
+                               rbf=rbf, max_degree=int(g["max_degree"]))
+        d = np.max(np.abs(sol.vals - g["u"][s + 1])) / np.max(np.abs(g["u"][s + 1]))
+        print("step %d product-vs-reference %.2e" % (s + 1, d))
+        assert d <= 1e-8, (s, d)
+        if s > 0:
+            assert _lib.profile_read("gemm")[2] == 0 and _lib.profile_read("panel")[2] == 0 and _lib.profile_read("assemble")[2] == 0
+    _lib.profile_enable(False)
+    u.clear_cache()

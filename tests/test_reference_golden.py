@@ -322,3 +322,24 @@ def test_reference_style_operators_with_a_foreign_array_library_lower_through_nu
     the demo's own text (demos/NavierStokes/30_channel_flow_blowing_suction.py:61-65)."""
     r = _run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "lowering_with_foreign_arrays.py")], ROOT, 600)
     assert r.returncode == 0 and "OK bc + rhs" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_oracle_time_steps_match_the_reference_advection_demo(oracle):
+    """Config 2 as the reference's demo defines it (demos/Advection/01_adv_diff_periodic.py:34-113: 35x35 doubly periodic
+    cloud, K = 0.08, VEL = (100, 0), DT = 1e-4, gaussian bump; definitions executed from the demo's source by the
+    generator): three implicit steps, each restated on the oracle from the reference's previous field."""
+    g = rc.load("ref_config2_advdiff_3steps")
+    cloud = oracle.RefSquareCloud(35, 35, {"South": "p1", "North": "p1", "West": "p2", "East": "p2"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert list(cloud.Np) == [70, 66] and int(g["max_degree"]) == 0
+    DT, K, VEL = float(g["DT"]), float(g["K"]), g["VEL"]
+    coef = np.tile([1 / DT, VEL[0], VEL[1], -K, -K], (cloud.Ni, 1))
+    A = oracle.assemble_A(cloud, "polyharmonic", 1, 1)
+    zero_bc = {k: np.zeros(len(cloud.facet_nodes[k])) for k in cloud.facet_types}
+    xy = cloud.sorted_nodes
+    assert np.allclose(g["u"][0], np.exp(-((xy[:, 0] - 0.35) ** 2 + (xy[:, 1] - 0.5) ** 2) / (2 * 0.1 ** 2)), rtol=1e-14, atol=1e-16)
+    for s in range(g["u"].shape[0] - 1):
+        cprev = np.linalg.solve(A, np.concatenate([g["u"][s], np.zeros(1)]))
+        q_int = oracle.eval_field(xy[:cloud.Ni], xy, cprev, "polyharmonic", 1, "value") / DT
+        vals, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 0, coef, oracle.assemble_q(cloud, q_int, zero_bc))
+        assert np.max(np.abs(vals - g["u"][s + 1])) <= 1e-8 * np.max(np.abs(g["u"][s + 1])), s
