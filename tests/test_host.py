@@ -507,3 +507,28 @@ def test_explicit_assembly_names_exist_and_refuse_large_clouds():
     assert np.array_equal(_betas(cloud, None), np.zeros(cloud.Nr))
     with pytest.raises(ValueError):
         _betas(cloud, {ids[0]: 1.0})
+
+
+def test_cloud_plotting_helpers_of_the_reference_surface():
+    """visualize_cloud / visualize_normals / visualize_field / average_spacing exist with the reference's signatures
+    (cloud.py:62-70, :175-285; the README example ends with cloud.visualize_field(...)).  Host-only: without matplotlib
+    they raise ImportError; with a pyplot module they draw (here: the no-op stand-in of oracle/refshim, in a subprocess)."""
+    import importlib.util
+    import subprocess
+    cloud = u.SquareCloud(Nx=5, Ny=4, facet_types=CONFIG1_FACETS)
+    xy = cloud.sorted_nodes
+    d = np.sqrt(((xy[:, None] - xy[None]) ** 2).sum(-1))
+    assert np.isclose(cloud.average_spacing(), d[np.triu_indices(cloud.N)].mean(), rtol=1e-15)
+    if importlib.util.find_spec("matplotlib") is None:
+        with pytest.raises(ImportError):
+            cloud.visualize_field(np.zeros(cloud.N))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, updes_b200 as u\n"
+            "c = u.SquareCloud(Nx=6, Ny=5, facet_types={'South': 'n', 'West': 'd', 'North': 'r', 'East': 'd'})\n"
+            "c.visualize_cloud(s=6); c.visualize_normals()\n"
+            "ax, img = c.visualize_field(np.arange(c.N, dtype=float), cmap='jet', projection='3d', title='RBF solution')\n"
+            "ax, img = c.visualize_field(np.arange(c.N, dtype=float)[:, None], levels=20)\n"
+            "print('drawn')\n" % (root, os.path.join(root, "oracle", "refshim")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "drawn" in r.stdout, r.stderr[-1500:]

@@ -117,6 +117,92 @@ class Cloud:
         items = sorted(dictionary.items(), key=lambda kv: kv[0])
         return np.stack([np.asarray(v) for _, v in items], axis=0)
 
+    # ---- plotting helpers of the reference surface (cloud.py:175-375): host-only, outside the hot path -------------
+    @staticmethod
+    def _pyplot():
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as e:
+            raise ImportError("Cloud.visualize_* needs matplotlib, which is not installed; the solver itself does not") from e
+        return plt
+
+    def average_spacing(self):
+        """Mean distance over all node pairs, the node itself included (cloud.py:62-70)."""
+        xy = np.asarray(self.sorted_nodes)
+        d = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+        iu = np.triu_indices(self.N)
+        return float(d[iu].mean())
+
+    def visualize_cloud(self, ax=None, title="Cloud", xlabel=r"$x$", ylabel=r"$y$", legend_size=8, figsize=(5.5, 5), **kwargs):
+        """Scatter plot of the nodes coloured by type (cloud.py:175-206)."""
+        plt = self._pyplot()
+        if ax is None:
+            ax = plt.figure(figsize=figsize).add_subplot(1, 1, 1)
+        xy = np.asarray(self.sorted_nodes)
+        Ni, Nd, Nn = self.Ni, self.Nd, self.Nn
+        for lo, hi, colour, label in ((0, Ni, "w", "internal"), (Ni, Ni + Nd, "r", "dirichlet"), (Ni + Nd, Ni + Nd + Nn, "g", "neumann"),
+                                      (Ni + Nd + Nn, self.N, "b", "robin")):
+            if hi > lo:
+                ax.scatter(x=xy[lo:hi, 0], y=xy[lo:hi, 1], c=colour, label=label, **kwargs)
+        if xlabel:
+            ax.set_xlabel(xlabel)
+        if ylabel:
+            ax.set_ylabel(ylabel)
+        ax.set_title(title)
+        ax.legend(bbox_to_anchor=(1.0, 0.5), loc="center left", prop={"size": legend_size})
+        plt.tight_layout()
+        return ax
+
+    def visualize_normals(self, ax=None, title="Normal vectors", xlabel=r"$x$", ylabel=r"$y$", figsize=(5.5, 5), zoom_region=None, **kwargs):
+        """Outward normals on Neumann / Robin / periodic nodes (cloud.py:209-238)."""
+        plt = self._pyplot()
+        if ax is None:
+            ax = plt.figure(figsize=figsize).add_subplot(1, 1, 1)
+        normals = np.asarray(self.sorted_outward_normals, dtype=np.float64).reshape(-1, 2)
+        if normals.shape[0] == 0:
+            return ax
+        first = self.Ni + self.Nd
+        xy = np.asarray(self.sorted_nodes)[first:first + normals.shape[0]]
+        q = ax.quiver(xy[:, 0], xy[:, 1], normals[:, 0] / 100, normals[:, 1] / 100, color="w", label="normals", **kwargs)
+        ax.quiverkey(q, X=0.5, Y=1.1, U=1, label="Normals", labelpos="E")
+        ax.scatter(x=xy[:, 0], y=xy[:, 1], c="m", **kwargs)
+        if xlabel:
+            ax.set_xlabel(xlabel)
+        if ylabel:
+            ax.set_ylabel(ylabel)
+        ax.set_title(title)
+        if zoom_region:
+            ax.set_xlim((zoom_region[0], zoom_region[1]))
+            ax.set_ylim((zoom_region[2], zoom_region[3]))
+        plt.tight_layout()
+        return ax
+
+    def visualize_field(self, field, projection="2d", title="Field", xlabel=r"$x$", ylabel=r"$y$", levels=50, colorbar=True, ax=None,
+                        figsize=(6, 5), extend="neither", **kwargs):
+        """Filled contours (2d) or a triangulated surface (3d) of a nodal field (cloud.py:241-285); returns (ax, image)."""
+        plt = self._pyplot()
+        xy = np.asarray(self.sorted_nodes)
+        field = np.asarray(field, dtype=np.float64)
+        if field.ndim > 1:
+            field = field[:, 0, ...]
+        if ax is None:
+            fig = plt.figure(figsize=figsize)
+            ax = fig.add_subplot(1, 1, 1, projection="3d") if projection == "3d" else fig.add_subplot(1, 1, 1)
+        if projection == "3d":
+            img = ax.plot_trisurf(xy[:, 0], xy[:, 1], field, **kwargs)
+        else:
+            img = ax.tricontourf(xy[:, 0], xy[:, 1], field, levels=levels, extend=extend, **kwargs)
+        if colorbar and projection != "3d":
+            plt.sca(ax)
+            plt.colorbar(img, extend=extend)
+        if xlabel:
+            ax.set_xlabel(xlabel)
+        if ylabel:
+            ax.set_ylabel(ylabel)
+        ax.set_title(title)
+        plt.tight_layout()
+        return ax, img
+
 
 class SquareCloud(Cloud):
     """Regular or jittered grid on the unit square (reference cloud.py:378-510).
