@@ -55,8 +55,16 @@ def ones(shape, dtype=None):
     return torch.ones(shape, dtype=_dtype(dtype) or _F64)
 
 
+def _as_int(v):
+    if callable(v):                    # `x.size` is an int on a jax / numpy array and a method on a tensor
+        v = v()
+    if isinstance(v, torch.Size):
+        return int(_np.prod(tuple(v), dtype=_np.int64))
+    return int(v)
+
+
 def arange(*a, dtype=None):
-    return torch.arange(*[int(v) for v in a], dtype=_dtype(dtype) or _I64)
+    return torch.arange(*[_as_int(v) for v in a], dtype=_dtype(dtype) or _I64)
 
 
 def linspace(a, b, n):

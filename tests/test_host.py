@@ -532,3 +532,19 @@ def test_cloud_plotting_helpers_of_the_reference_surface():
             "print('drawn')\n" % (root, os.path.join(root, "oracle", "refshim")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "drawn" in r.stdout, r.stderr[-1500:]
+
+
+def test_small_host_utilities_of_the_reference_surface(tmp_path):
+    """make_dir / random_name / dot_vec / dot_mat / RK4 (updes/utils.py:152-246, operators.py:777-779): every demo script of
+    the reference calls some of them next to the solver."""
+    d = str(tmp_path / "run")
+    u.make_dir(d); u.make_dir(d)
+    assert os.path.isdir(d) and len(u.random_name(7)) == 7 and u.random_name().isdigit()
+    a, b = np.arange(6.0).reshape(3, 2), np.ones((3, 2))
+    assert np.array_equal(u.dot_vec(a, b), a.sum(1)) and np.array_equal(u.dot_mat(np.tile(2 * np.eye(2), (3, 1, 1)), a), 2 * a)
+    te = np.linspace(0, 1, 11)
+    ys = u.RK4(lambda t, y: -y, (0.0, 1.0), np.array([1.0, 3.0]), t_eval=te, subdivisions=4)
+    assert ys.shape == (11, 2) and np.allclose(ys[:, 0], np.exp(-te), rtol=1e-7) and np.array_equal(ys[0], [1.0, 3.0])
+    assert u.RK4(lambda t, y: -y, (0.0, 1.0), np.array([1.0])).shape == (2, 1)
+    with pytest.raises(ValueError):
+        u.RK4(lambda t, y: -y, (0.0, None), np.array([1.0]))

@@ -18,6 +18,7 @@ from .operators import (BatchPoints, OperatorLoweringError, SteadySol, assemble_
                         zerofy_periodic_cond)
 
 from .autodiff import linear_solve
+from .utils import RK4, dot_mat, dot_vec, make_dir, print_line_by_line, random_name
 from .explicit import (assemble_A, assemble_B, assemble_P, assemble_Phi, assemble_bd_Phi_P, assemble_invert_A,
                        assemble_op_Phi_P)
 
