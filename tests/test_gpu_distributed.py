@@ -134,3 +134,47 @@ def test_block_cyclic_lu_world1(tmp_path, nx, nb):
 @pytest.mark.parametrize("nx,nb", [(24, 64), (40, 128), (64, 512)])
 def test_block_cyclic_lu_world2(tmp_path, nx, nb):
     _run(2, nx, nb, tmp_path)
+
+
+def _worker_api(rank, world, port, grid, out):
+    """The public API on the sharded path: pde_solver_jit after enable_distributed(), called twice (the second
+    call used to run out of memory because the first solution pinned its factors), against the single-GPU path."""
+    import torch
+    import torch.distributed as dist
+    import updes_b200 as u
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cloud = u.SquareCloud(Nx=40, Ny=30, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})
+        op = lambda x, center, rbf, monomial, fields: u.nodal_laplacian(x, center, rbf, monomial)
+        rhs = lambda x, centers, rbf, fields: 0.0
+        bcs = {"South": lambda c: 0.0, "West": lambda c: 0.0, "North": lambda c: np.sin(np.pi * c[0]), "East": lambda c: 0.0}
+        single = u.pde_solver_jit(op, rhs, cloud, bcs, u.polyharmonic, 1)
+        u.enable_distributed(grid=grid)
+        sols = []
+        for _ in range(2):
+            u.clear_cache()
+            sols.append(u.pde_solver_jit(op, rhs, cloud, bcs, u.polyharmonic, 1))
+        cached = u.pde_solver_jit(op, rhs, cloud, bcs, u.polyharmonic, 1)            # third call: factor cache hit
+        u.disable_distributed()
+        scale = np.max(np.abs(single.vals))
+        res = [float(np.max(np.abs(s.vals - single.vals)) / scale) for s in sols + [cached]]
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+        if rank == 0:
+            np.save(out, np.array(allres))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid", [(2, None), (2, (2, 1)), (4, (2, 2))])
+def test_public_api_on_the_sharded_path(tmp_path, world, grid):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker_api, args=(world, _free_port(), grid, out), nprocs=world, join=True)
+    r = np.load(out)
+    assert np.all(r <= 1e-8), r          # same discrete solution as the single-GPU path on every rank, every call
