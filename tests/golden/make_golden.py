@@ -8,8 +8,10 @@ container, where /root/reference is mounted):
                            oracle's literal restatement of GmshCloud (sorted nodes, normals, counts,
                            facet nodes) for the two facet-type sets of demos/NavierStokes/30_...:40-41
 
-The reference itself cannot be imported (no JAX in the image), so the vectors come from the oracle; the
-mesh fixture is the one piece of reference *data* on this path and is stored in parsed form only.
+These vectors come from the ORACLE (round 1, when the reference could not be run here).  The files made by the reference's
+own code are tests/golden/ref_*.npz (make_reference_golden.py); tests/test_reference_golden.py checks that both agree
+(cloud arrays bit for bit, the config-1 solution to 8e-10).  The mesh fixture is the one piece of reference *data* on
+this path and is stored in parsed form only.
 """
 import os
 import sys

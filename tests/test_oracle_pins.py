@@ -1,8 +1,8 @@
 """Pin the CPU oracle (CPU only, no GPU): closed forms vs autodiff restatement, the reference's own
 three known-answer tests restated through the oracle, and the analytic Laplace solution.
 
-The reference cannot be imported in this image (no jax/jaxlib/lineax) and holds no golden matrices,
-so per-entry parity with its JAX x64 path is 'parity unpinned'; these are the pins that exist."""
+These pins predate tests/test_reference_golden.py, which checks the oracle against golden vectors produced by the
+reference's own code (run over the JAX-API stand-in of oracle/refshim); they stay as independent second opinions."""
 import os
 from functools import partial
 
