@@ -343,3 +343,46 @@ def test_oracle_time_steps_match_the_reference_advection_demo(oracle):
         q_int = oracle.eval_field(xy[:cloud.Ni], xy, cprev, "polyharmonic", 1, "value") / DT
         vals, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 0, coef, oracle.assemble_q(cloud, q_int, zero_bc))
         assert np.max(np.abs(vals - g["u"][s + 1])) <= 1e-8 * np.max(np.abs(g["u"][s + 1])), s
+
+
+def test_reference_quirks_are_facts_of_the_reference_output():
+    """SURVEY.md Q1-Q4 read off the reference's own matrices (not off the restatement): Q1 the diagonal of Phi is 0 even
+    where phi(0) = 1 (the node is dropped from its own support, cloud.py:110-112); Q2 periodic rows do write their own
+    column; Q3 Robin rows of bd(Phi) use the Neumann nodes' normal slots when Nn > 0 (assembly.py:206); Q4 derivatives
+    at r = 0 are 0 (nan_to_num) in the field evaluators."""
+    g = rc.load("ref_kernels_7x6")
+    N = g["sorted_nodes"].shape[0]
+    for name in ("gaussian", "multiquadric", "inverse_multiquadric"):                    # phi(0) = 1 for these
+        Phi = g[name + "_A"][:N, :N]
+        assert np.all(np.diag(Phi) == 0.0) and np.all(Phi[~np.eye(N, dtype=bool)] != 0.0)
+    g = rc.load("ref_periodic_10x10")
+    Ni = int(g["counts"][1])
+    assert np.allclose([g["bdPhi"][k, Ni + k] for k in range(10)], -1.0)       # phi(0) - phi(1) with phi = r^3: own column written
+    # Q3: on the 11x8 Robin + Neumann cloud the first Robin row (West facet, true normal (-1, 0)) carries the South facet's
+    # normal (0, -1): with beta known, (row - beta * phi) must equal grad(phi) . (0, -1), not grad(phi) . (-1, 0)
+    g = rc.load("ref_robin_11x8")
+    Ni, Nd, Nn = (int(v) for v in g["counts"][1:4])
+    xy, eps = g["sorted_nodes"], 3.0
+    i = Ni + Nd + Nn                                                           # first Robin node
+    assert np.allclose(g["sorted_outward_normals"][0], [0.0, -1.0]) and np.allclose(g["sorted_outward_normals"][Nn], [-1.0, 0.0])
+    d = xy[i] - xy                                                             # x_i - x_j
+    phi = np.exp(-eps ** 2 * (d ** 2).sum(1))
+    grad = -2 * eps ** 2 * d * phi[:, None]
+    row = g["bdPhi"][i - Ni]
+    cols = np.arange(xy.shape[0]) != i
+    quirk = g["betas"][0] * phi + grad @ np.array([0.0, -1.0])
+    true_normal = g["betas"][0] * phi + grad @ np.array([-1.0, 0.0])
+    assert np.allclose(row[cols], quirk[cols], rtol=1e-12, atol=1e-15) and not np.allclose(row[cols], true_normal[cols], rtol=1e-3, atol=1e-6)
+    # Q4: the Laplacian of a gaussian field evaluated AT a node omits that node's own term (true value -4 eps^2 c_i)
+    g = rc.load("ref_kernels_7x6")
+    xy, pts, c, eps = g["sorted_nodes"], g["eval_pts"], g["gaussian_coeffs"], 4.0
+    N = xy.shape[0]
+    k = 0                                                                       # eval_pts[0] is node 0
+    assert np.array_equal(pts[k], xy[0])
+    s = ((pts[k] - xy) ** 2).sum(1)
+    lap_terms = (4 * eps ** 4 * s - 4 * eps ** 2) * np.exp(-eps ** 2 * s) * c[:N]
+    poly = 2 * c[N + 3] + 2 * c[N + 5] + 6 * c[N + 6] * pts[k, 0] + 2 * c[N + 7] * pts[k, 1] + 2 * c[N + 8] * pts[k, 0] + 6 * c[N + 9] * pts[k, 1] \
+        + 12 * c[N + 10] * pts[k, 0] ** 2 + 6 * c[N + 11] * pts[k, 0] * pts[k, 1] + 2 * c[N + 12] * (pts[k, 0] ** 2 + pts[k, 1] ** 2) \
+        + 6 * c[N + 13] * pts[k, 0] * pts[k, 1] + 12 * c[N + 14] * pts[k, 1] ** 2
+    with_self, without_self = lap_terms.sum() + poly, lap_terms.sum() - lap_terms[0] + poly
+    assert np.isclose(g["gaussian_laplacian"][k], without_self, rtol=1e-10) and not np.isclose(g["gaussian_laplacian"][k], with_self, rtol=1e-6)
