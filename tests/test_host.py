@@ -548,3 +548,16 @@ def test_small_host_utilities_of_the_reference_surface(tmp_path):
     assert u.RK4(lambda t, y: -y, (0.0, 1.0), np.array([1.0])).shape == (2, 1)
     with pytest.raises(ValueError):
         u.RK4(lambda t, y: -y, (0.0, None), np.array([1.0]))
+
+
+def test_support_size_selects_only_the_global_path():
+    """The reference turns 'max' into N (cloud.py:97-98) and then drops the node itself; N - 1 already drops the farthest
+    node of every support (RBF-FD), which is out of scope and must be refused, not silently treated as global."""
+    ft = {"South": "n", "West": "d", "North": "n", "East": "d"}
+    for ss in ("max", None, 64):
+        assert u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss).N == 64
+    for ss in (63, 10):
+        with pytest.raises(NotImplementedError):
+            u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss)
+    with pytest.raises(ValueError):
+        u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size="all")

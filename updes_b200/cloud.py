@@ -25,10 +25,11 @@ class Cloud:
     """Base bookkeeping shared by all clouds (reference cloud.py:10-50)."""
 
     def __init__(self, facet_types, support_size="max"):
-        if support_size not in ("max", None):
-            raise NotImplementedError(
-                "updes_b200 implements the global collocation path only (support_size='max'); "
-                "local RBF-FD supports are out of scope (reference README lists them as ill-conditioned)")
+        # "max", None, or the number of nodes N (what the reference turns "max" into, cloud.py:97-98) select the global
+        # path; anything smaller drops the farthest nodes from every support (RBF-FD): checked once N is known
+        if not (support_size in ("max", None) or (isinstance(support_size, (int, np.integer)) and not isinstance(support_size, bool))):
+            raise ValueError("support_size must be 'max', None or an integer, got %r" % (support_size,))
+        self._requested_support = support_size
         self.support_size = "max"
         self.N = self.Ni = self.Nd = self.Nr = self.Nn = 0
         self.Np = []
@@ -43,6 +44,11 @@ class Cloud:
     # -- renumbering (cloud.py:115-172) -----------------------------------------------------------
     def _renumber(self, types, coords, normals_by_old, facet_nodes_old):
         """types: array of str per original id; returns the sorted arrays and fills the dicts."""
+        req = getattr(self, "_requested_support", "max")
+        if req not in ("max", None) and int(req) != len(coords):
+            raise NotImplementedError(
+                "updes_b200 implements the global collocation path only (support_size='max' or N = %d, got %d); "
+                "local RBF-FD supports are out of scope (reference README lists them as ill-conditioned)" % (len(coords), int(req)))
         N = len(types)
         first = np.array([t[0] for t in types])
         order = [np.flatnonzero(first == c) for c in ("i", "d", "n", "r")]
