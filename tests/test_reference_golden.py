@@ -386,3 +386,11 @@ def test_reference_quirks_are_facts_of_the_reference_output():
         + 6 * c[N + 13] * pts[k, 0] * pts[k, 1] + 12 * c[N + 14] * pts[k, 1] ** 2
     with_self, without_self = lap_terms.sum() + poly, lap_terms.sum() - lap_terms[0] + poly
     assert np.isclose(g["gaussian_laplacian"][k], without_self, rtol=1e-10) and not np.isclose(g["gaussian_laplacian"][k], with_self, rtol=1e-6)
+
+
+def test_stand_in_has_the_jax_semantics_the_hot_path_relies_on():
+    """x64 dtypes, functional .at[].set, NaN gradients of the distance at coincident points + nan_to_num, jacfwd(grad),
+    vmap with in_axes=None and Python-number outputs, fori_loop / Partial / tree_map, LAPACK inv, QR solve
+    (tests/refshim_semantics.py, in a subprocess because it imports the stand-in)."""
+    r = _run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "refshim_semantics.py")], ROOT, 300)
+    assert r.returncode == 0 and "SEMANTICS OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
