@@ -63,6 +63,8 @@ def _worker(rank, P, Q, port, n, nb, seed, equil, out):
     (1, 3, 170, 32, False),     # degenerates to the 1 x Q layout
     (3, 1, 170, 32, False),     # P x 1: every panel gathered from all ranks
     (2, 2, 96, 32, False),      # fewer blocks than 2 per process
+    (2, 4, 300, 32, True),      # the 8-GPU grid of SURVEY.md 8(e)
+    (4, 2, 270, 32, False),
 ])
 def test_grid2d_lu_matches_lapack(tmp_path, P, Q, n, nb, equil):
     import scipy.linalg as sla
