@@ -561,3 +561,34 @@ def test_support_size_selects_only_the_global_path():
             u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss)
     with pytest.raises(ValueError):
         u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size="all")
+
+
+def test_symbolic_and_numeric_lowering_agree_on_random_linear_operators():
+    """Random operators a0 phi + a1 phi_x + a2 phi_y + a3 phi_xx + a4 phi_yy with coefficients mixing constants, x and
+    fields: the symbolic path and the numeric-probe path (forced by converting the terms to numbers) give the same table."""
+    rng = np.random.default_rng(5)
+    cloud = u.SquareCloud(Nx=7, Ny=6, facet_types=CONFIG1_FACETS)
+    Ni = cloud.Ni
+    F = rng.normal(size=(3, cloud.N))
+    for trial in range(8):
+        w = rng.normal(size=(5, 3))                       # weights of (1, x[0], fields[trial % 3]) per coefficient
+
+        def coeffs(x, f, k):
+            return w[k, 0] + w[k, 1] * x[0] + w[k, 2] * f[trial % 3]
+
+        def symbolic(x, c, r, m, f):
+            g = u.nodal_gradient(x, c, r, m)
+            return (coeffs(x, f, 0) * u.nodal_value(x, c, r, m) + coeffs(x, f, 1) * g[0] + coeffs(x, f, 2) * g[1]
+                    + u.nodal_div_grad(x, c, r, m, (coeffs(x, f, 3), coeffs(x, f, 4))))
+
+        def numeric(x, c, r, m, f):
+            g = np.asarray(u.nodal_gradient(x, c, r, m), dtype=float)             # leaves the symbolic world
+            return (coeffs(x, f, 0) * float(u.nodal_value(x, c, r, m)) + coeffs(x, f, 1) * g[0] + coeffs(x, f, 2) * g[1]
+                    + u.nodal_div_grad(x, c, r, m, (coeffs(x, f, 3), coeffs(x, f, 4))))
+
+        a, ap = u.lower_diff_operator(symbolic, cloud, u.gaussian, list(F))
+        b, bp = u.lower_diff_operator(numeric, cloud, u.gaussian, list(F))
+        xs = cloud.sorted_nodes[:Ni, 0]
+        want = np.stack([w[k, 0] + w[k, 1] * xs + w[k, 2] * F[trial % 3, :Ni] for k in range(5)], axis=1)
+        assert np.allclose(a, want, rtol=1e-14, atol=1e-15) and np.allclose(b, want, rtol=1e-14, atol=1e-15)
+        assert np.array_equal(a, ap) and np.array_equal(b, bp)
