@@ -22,6 +22,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
                           all kernels and degrees 0-4, fully general operator with five nodal fields: diffMat of each
   ref_generated_msh       GmshCloud on two channel meshes written by tests/golden/make_msh.py, two facet-type orders
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
+  ref_laplace_demo_30x30  demos/Laplace/00_laplace_with_rbf.py run unmodified as a whole script: solution, Laplacian at the nodes, its printed errors
   ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
@@ -321,6 +322,27 @@ def case_multi(nb_iters=3):
     return out
 
 
+def case_laplace_demo():
+    """demos/Laplace/00_laplace_with_rbf.py run UNMODIFIED, whole script (runpy, in a scratch directory because it creates
+    ./data/TempFolder; its plotting calls go to the no-op pyplot stand-in): 30x30 Laplace problem, the solution, the
+    Laplacian of the solution at the nodes, and the two error figures the script prints."""
+    import runpy
+    import tempfile
+    demo = os.path.join(REFERENCE, "demos/Laplace/00_laplace_with_rbf.py")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.mkdir(os.path.join(d, "data"))
+        os.chdir(d)
+        try:
+            ns = runpy.run_path(demo, run_name="__main__")
+        finally:
+            os.chdir(cwd)
+    cloud, sol = ns["cloud"], ns["sol"]
+    return dict(cloud_arrays(cloud), vals=npa(sol.vals), coeffs=npa(sol.coeffs), laplacian_at_nodes=npa(ns["lap"]),
+                exact=npa(ns["exact_sol"]), mse_total=np.array(float(jnp.mean(ns["error"] ** 2))),
+                mse_neumann=np.array(float(jnp.mean(ns["error_neumann"] ** 2))))
+
+
 def case_config2(nb_steps=3):
     """Config 2 as the reference's demo defines it: constants, cloud (35x35, doubly periodic, key = None), operators and
     initial field are the source text of demos/Advection/01_adv_diff_periodic.py:34-93 executed unchanged; the time loop
@@ -365,7 +387,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
+         "ref_laplace_demo_30x30": case_laplace_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
 
 
 def main():

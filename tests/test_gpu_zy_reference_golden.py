@@ -260,3 +260,22 @@ def test_config2_time_steps_against_the_reference_advection_demo():
             assert _lib.profile_read("gemm")[2] == 0 and _lib.profile_read("panel")[2] == 0 and _lib.profile_read("assemble")[2] == 0
     _lib.profile_enable(False)
     u.clear_cache()
+
+
+def test_laplace_demo_30x30_against_the_unmodified_reference_script():
+    """The reference's Laplace demo (demos/Laplace/00_laplace_with_rbf.py, run unmodified by the golden generator): same
+    30x30 problem through the product -- solution within 1e-8, the error figures the script prints, and the Laplacian of
+    the solution at the nodes through the matrix-free evaluator."""
+    g = rc.load("ref_laplace_demo_30x30")
+    case = rc.laplace(u, 30, 30)
+    cloud = u.SquareCloud(**case.cloud_args)
+    rc.assert_cloud_equals_golden(cloud, g)
+    rbf = partial(u.polyharmonic, a=1)
+    sol = u.pde_solver_jit(diff_operator=case.op, rhs_operator=lambda x, centers=None, rbf=None, fields=None: -0.0, cloud=cloud,
+                           boundary_conditions=case.bcs, rbf=rbf, max_degree=1)
+    assert np.max(np.abs(sol.vals - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))
+    south = np.asarray(cloud.facet_nodes["South"])
+    assert np.isclose(np.mean((g["exact"] - sol.vals) ** 2), float(g["mse_total"]), rtol=1e-5)
+    assert np.isclose(np.mean((g["exact"][south] - sol.vals[south]) ** 2), float(g["mse_neumann"]), rtol=1e-5)
+    lap = u.laplacian_vec(cloud.sorted_nodes, g["coeffs"], cloud.sorted_nodes, rbf)
+    assert np.max(np.abs(lap - g["laplacian_at_nodes"])) <= 1e-10 * np.max(np.abs(g["laplacian_at_nodes"]))

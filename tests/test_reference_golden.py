@@ -394,3 +394,23 @@ def test_stand_in_has_the_jax_semantics_the_hot_path_relies_on():
     (tests/refshim_semantics.py, in a subprocess because it imports the stand-in)."""
     r = _run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "refshim_semantics.py")], ROOT, 300)
     assert r.returncode == 0 and "SEMANTICS OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_oracle_matches_the_unmodified_laplace_demo(oracle):
+    """demos/Laplace/00_laplace_with_rbf.py, the whole script run unmodified by the generator (30x30): its solution, the
+    Laplacian of its solution at the nodes (r = 0 terms dropped by nan_to_num), and the mean-square errors it prints."""
+    g = rc.load("ref_laplace_demo_30x30")
+    cloud = oracle.RefSquareCloud(30, 30, {"South": "n", "West": "d", "North": "d", "East": "d"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    xy = cloud.sorted_nodes
+    bc = {f: (np.sin(np.pi * xy[ids, 0]) if f == "North" else np.zeros(len(ids))) for f, ids in cloud.facet_nodes.items()}
+    vals, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, 1, np.tile([0.0, 0, 0, 1.0, 1.0], (cloud.Ni, 1)),
+                                        oracle.assemble_q(cloud, np.zeros(cloud.Ni), bc))
+    assert np.max(np.abs(vals - g["vals"])) <= 1e-8 * np.max(np.abs(g["vals"]))
+    exact = np.sin(np.pi * xy[:, 0]) * np.cosh(np.pi * xy[:, 1]) / np.cosh(np.pi)
+    assert np.allclose(exact, g["exact"], rtol=1e-14, atol=1e-16)
+    assert np.isclose(np.mean((exact - vals) ** 2), float(g["mse_total"]), rtol=1e-5)                 # the figure the demo prints
+    south = np.asarray(cloud.facet_nodes["South"])
+    assert np.isclose(np.mean((exact[south] - vals[south]) ** 2), float(g["mse_neumann"]), rtol=1e-5)
+    lap = oracle.eval_field(xy, xy, g["coeffs"], "polyharmonic", 1, "laplacian")
+    assert np.max(np.abs(lap - g["laplacian_at_nodes"])) <= 1e-11 * np.max(np.abs(g["laplacian_at_nodes"]))
