@@ -141,6 +141,13 @@ def allclose(a, b, rtol=1e-05, atol=1e-08):
     return bool(torch.allclose(a.to(_F64), b.to(_F64).expand_as(a) if b.dim() == 0 else b.to(_F64), rtol=rtol, atol=atol))
 
 
+def where(cond, a, b):
+    cond = array(cond)
+    like = a if isinstance(a, torch.Tensor) else (b if isinstance(b, torch.Tensor) else None)
+    dt = like.dtype if like is not None else _F64
+    return torch.where(cond, torch.as_tensor(a, dtype=dt), torch.as_tensor(b, dtype=dt))
+
+
 def trace(x):
     return torch.trace(x)
 
@@ -204,6 +211,7 @@ class _AtIdx:
 
 
 torch.Tensor.at = property(lambda self: _At(self))
+torch.Tensor.copy = lambda self: self.clone()          # jax arrays have .copy()
 
 
 def _numpy_style(name):

@@ -23,6 +23,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_generated_msh       GmshCloud on two channel meshes written by tests/golden/make_msh.py, two facet-type orders
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
   ref_laplace_demo_30x30  demos/Laplace/00_laplace_with_rbf.py run unmodified as a whole script: solution, Laplacian at the nodes, its printed errors
+  ref_darcy_demo_20x20    demos/Darcy/00_darcy_flow.py run unmodified: identity-operator solve (polyharmonic a=2) and -div(k grad u) = 1 (thin_plate a=3)
   ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
@@ -343,6 +344,31 @@ def case_laplace_demo():
                 mse_neumann=np.array(float(jnp.mean(ns["error_neumann"] ** 2))))
 
 
+def _run_demo_unmodified(relpath):
+    """runpy of a reference demo script in a scratch directory (the demos create ./data/<run name>/ and save figures
+    through the no-op pyplot stand-in); returns the script's global namespace."""
+    import runpy
+    import tempfile
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.mkdir(os.path.join(d, "data"))
+        os.chdir(d)
+        try:
+            return runpy.run_path(os.path.join(REFERENCE, relpath), run_name="__main__")
+        finally:
+            os.chdir(cwd)
+
+
+def case_darcy_demo():
+    """demos/Darcy/00_darcy_flow.py run UNMODIFIED (20x20, all Dirichlet): (1) the permeability field passed through an
+    identity-operator solve with polyharmonic a = 2, degree 2; (2) -div(k grad u) = 1 through nodal_div_grad with the
+    nodal field k as diff_args, thin_plate a = 3, degree 2."""
+    ns = _run_demo_unmodified("demos/Darcy/00_darcy_flow.py")
+    cloud, perm, uf = ns["cloud"], ns["perm_field"], ns["ufield"]
+    return dict(cloud_arrays(cloud), permeability=npa(ns["permeability"]), perm_vals=npa(perm.vals), perm_coeffs=npa(perm.coeffs),
+                u_vals=npa(uf.vals), u_coeffs=npa(uf.coeffs), max_degree=np.array(ns["MAX_DEGREE"]))
+
+
 def case_config2(nb_steps=3):
     """Config 2 as the reference's demo defines it: constants, cloud (35x35, doubly periodic, key = None), operators and
     initial field are the source text of demos/Advection/01_adv_diff_periodic.py:34-93 executed unchanged; the time loop
@@ -387,7 +413,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_laplace_demo_30x30": case_laplace_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
+         "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
 
 
 def main():

@@ -279,3 +279,43 @@ def test_laplace_demo_30x30_against_the_unmodified_reference_script():
     assert np.isclose(np.mean((g["exact"][south] - sol.vals[south]) ** 2), float(g["mse_neumann"]), rtol=1e-5)
     lap = u.laplacian_vec(cloud.sorted_nodes, g["coeffs"], cloud.sorted_nodes, rbf)
     assert np.max(np.abs(lap - g["laplacian_at_nodes"])) <= 1e-10 * np.max(np.abs(g["laplacian_at_nodes"]))
+
+
+def test_darcy_demo_against_the_unmodified_reference_script():
+    """The reference's Darcy demo (demos/Darcy/00_darcy_flow.py, run unmodified by the golden generator): -div(k grad u) = 1
+    through nodal_div_grad with the nodal permeability field as diff_args, thin_plate a = 3, degree 2, all Dirichlet, 20x20;
+    and the identity-operator solve (polyharmonic a = 2) that makes the permeability field."""
+    from helpers import backward_error, exact_solution
+    g = rc.load("ref_darcy_demo_20x20")
+    facets = {"South": "d", "North": "d", "West": "d", "East": "d"}
+    cloud = u.SquareCloud(Nx=20, Ny=20, facet_types=facets)
+    rc.assert_cloud_equals_golden(cloud, g)
+    zero = lambda p: 0.0
+    bcs = {k: zero for k in facets}
+
+    def check(sol, want, what):
+        d = np.max(np.abs(sol.vals - want)) / np.max(np.abs(want))
+        print("%s: product-vs-reference %.2e" % (what, d))
+        assert d <= 2e-7, (what, d)              # the reference goes through inv(A) at cond 1e9 - 1e10: its own error is ~2e-8
+
+    rbf1 = partial(u.polyharmonic, a=2)
+    perm = u.pde_solver_jit(diff_operator=lambda x, center=None, rbf=None, monomial=None, fields=None: u.nodal_value(x, center, rbf, monomial),
+                            rhs_operator=lambda x, centers=None, rbf=None, fields=None: u.value(x, fields[:, 0], centers, rbf),
+                            rhs_args=[g["permeability"]], cloud=cloud, boundary_conditions=bcs, rbf=rbf1, max_degree=2)
+    check(perm, g["perm_vals"], "permeability (identity operator)")
+
+    def darcy(x, center=None, rbf=None, monomial=None, fields=None):
+        perm_val = fields[0]
+        return -u.nodal_div_grad(x, center, rbf, monomial, (perm_val, perm_val))
+
+    rbf2 = partial(u.thin_plate, a=3)
+    sol = u.pde_solver_jit(diff_operator=darcy, rhs_operator=lambda x, centers=None, rbf=None, fields=None: 1.0,
+                           diff_args=[g["perm_vals"]], rhs_args=[g["perm_vals"]], cloud=cloud, boundary_conditions=bcs, rbf=rbf2, max_degree=2)
+    check(sol, g["u_vals"], "Darcy solution")
+    # and the product against the exactly solved discrete system built from the same inputs (north_star: 1e-8; backward error 1e-13)
+    K = np.asarray(u.assemble_A(cloud, rbf2, 6))          # [Phi P; P^T 0]: only used for vals = [Phi P] c below
+    coef, _ = u.lower_diff_operator(darcy, cloud, rbf2, [g["perm_vals"]])
+    Kd = _assemble(cloud, asm.build_operator_rows(cloud, coef), "thin_plate", 3, 6)
+    rhs = np.concatenate([np.ones(cloud.Ni), np.zeros(cloud.N - cloud.Ni), np.zeros(6)])
+    exact, _ = exact_solution(Kd, rhs, K[:cloud.N])
+    assert np.max(np.abs(sol.vals - exact)) <= 1e-8 * np.max(np.abs(exact)) and backward_error(Kd, sol.coeffs, rhs) <= 1e-13

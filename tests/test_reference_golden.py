@@ -414,3 +414,32 @@ def test_oracle_matches_the_unmodified_laplace_demo(oracle):
     assert np.isclose(np.mean((exact[south] - vals[south]) ** 2), float(g["mse_neumann"]), rtol=1e-5)
     lap = oracle.eval_field(xy, xy, g["coeffs"], "polyharmonic", 1, "laplacian")
     assert np.max(np.abs(lap - g["laplacian_at_nodes"])) <= 1e-11 * np.max(np.abs(g["laplacian_at_nodes"]))
+
+
+def test_oracle_matches_the_unmodified_darcy_demo(oracle):
+    """demos/Darcy/00_darcy_flow.py run unmodified by the generator (20x20, all Dirichlet): an identity-operator solve with
+    polyharmonic a = 2 and -div(k grad u) = 1 through nodal_div_grad with a nodal field, thin_plate a = 3, degree 2.
+    cond(A) ~ 1e9 - 1e10 here, so two inverse-based pipelines agree to a few 1e-8: the bound is 4x the sum of their own
+    distances from the exactly solved discrete system."""
+    g = rc.load("ref_darcy_demo_20x20")
+    cloud = oracle.RefSquareCloud(20, 20, {"South": "d", "North": "d", "West": "d", "East": "d"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    M, Ni, N = 6, cloud.Ni, cloud.N
+    zero_bc = {k: np.zeros(len(v)) for k, v in cloud.facet_nodes.items()}
+
+    def check(kind, a, coef, q, want, what):
+        vals, _, _ = oracle.reference_solve(cloud, kind, a, 2, coef, q)
+        K, A = oracle.assemble_K(cloud, kind, a, M, coef), oracle.assemble_A(cloud, kind, a, M)
+        exact, _ = exact_solution(K, np.concatenate([q, np.zeros(M)]), A[:N])
+        s = np.max(np.abs(exact))
+        e_gold, e_orc, d = np.max(np.abs(want - exact)) / s, np.max(np.abs(vals - exact)) / s, np.max(np.abs(vals - want)) / s
+        print("%s: reference-vs-exact %.2e oracle-vs-exact %.2e oracle-vs-reference %.2e" % (what, e_gold, e_orc, d))
+        assert d <= max(1e-8, 4.0 * (e_gold + e_orc)) and e_gold <= 1e-6, (what, d, e_gold, e_orc)
+
+    A1 = oracle.assemble_A(cloud, "polyharmonic", 2, M)
+    cperm = np.linalg.solve(A1, np.concatenate([g["permeability"], np.zeros(M)]))
+    q1 = oracle.assemble_q(cloud, oracle.eval_field(cloud.sorted_nodes[:Ni], cloud.sorted_nodes, cperm, "polyharmonic", 2, "value"), zero_bc)
+    check("polyharmonic", 2, np.tile([1.0, 0, 0, 0, 0], (Ni, 1)), q1, g["perm_vals"], "permeability (identity operator)")
+    k = g["perm_vals"][:Ni]
+    coef2 = np.stack([np.zeros(Ni), np.zeros(Ni), np.zeros(Ni), -k, -k], axis=1)
+    check("thin_plate", 3, coef2, oracle.assemble_q(cloud, np.ones(Ni), zero_bc), g["u_vals"], "Darcy solution")
