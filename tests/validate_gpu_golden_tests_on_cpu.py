@@ -6,7 +6,7 @@ refinement step, evaluators -> oracle.eval_field), and each test function is the
 LOGIC -- shapes, golden keys, tolerances with their margins, the host orchestration around the device calls -- not the
 kernels (those are checked against the same oracle on a GPU by the rest of the `-m gpu` suite).
 
-    python tools/validate_gpu_golden_tests_on_cpu.py
+    python tests/validate_gpu_golden_tests_on_cpu.py
 """
 import importlib
 import os
@@ -17,7 +17,7 @@ import scipy.linalg as sla
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # (this file lives in tests/: only tests/ may use the oracle)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from oracle import oracle as O  # noqa: E402
