@@ -10,7 +10,7 @@ RUN="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 case "${1:-one}" in
 one)
   # CUDA path against the reference-produced golden vectors, explicit assemble_* wrappers, 1x1 grid
-  timeout 400 python -m pytest tests/test_gpu_zy_reference_golden.py tests/test_gpu_zz_grid2d.py -q -m gpu -s > $O/r03_pytest_new.log 2>&1
+  timeout 400 python -m pytest tests/test_gpu_zy_reference_golden.py tests/test_gpu_zx_grid2d.py -q -m gpu -s > $O/r03_pytest_new.log 2>&1
   tail -5 $O/r03_pytest_new.log
   # ncu launch list of ONE whole default step (about 19 000 launches; per-launch times cold-cache and serialised: shares only)
   timeout 450 ncu --clock-control none --metrics gpu__time_duration.sum -c 25000 --csv --log-file $O/r03_launches_default.csv \
@@ -19,7 +19,7 @@ one)
   head -20 $O/r03_launches_default_summary.txt
   ;;
 four)
-  timeout 300 python -m pytest tests/test_gpu_zz_grid2d.py tests/test_gpu_distributed.py -q -m gpu > $O/r03_pytest_4gpu.log 2>&1
+  timeout 300 python -m pytest tests/test_gpu_zx_grid2d.py tests/test_gpu_distributed.py -q -m gpu > $O/r03_pytest_4gpu.log 2>&1
   tail -5 $O/r03_pytest_4gpu.log
   timeout 200 $RUN --nproc-per-node 4 --master-port 29541 tools/grid2d_gpu_check.py --grid 2x2 --cases 50x50:128,100x100:256 > $O/r03_grid2d_2x2.log 2>&1
   tail -4 $O/r03_grid2d_2x2.log
