@@ -22,6 +22,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
                           all kernels and degrees 0-4, fully general operator with five nodal fields: diffMat of each
   ref_generated_msh       GmshCloud on two channel meshes written by tests/golden/make_msh.py, two facet-type orders
   ref_multi_solver_9x8    pde_multi_solver on two genuinely coupled equations, the state after each of three sweeps
+  ref_integrals_12x12     the setting of updes/tests/test_integrals.py: coefficients of s = x^2/(1+y^2), the rebuilt field, integrate_field
   ref_laplace_demo_30x30  demos/Laplace/00_laplace_with_rbf.py run unmodified as a whole script: solution, Laplacian at the nodes, its printed errors
   ref_darcy_demo_20x20    demos/Darcy/00_darcy_flow.py run unmodified: identity-operator solve (polyharmonic a=2) and -div(k grad u) = 1 (thin_plate a=3)
   ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
@@ -369,6 +370,19 @@ def case_darcy_demo():
                 u_vals=npa(uf.vals), u_coeffs=npa(uf.coeffs), max_degree=np.array(ns["MAX_DEGREE"]))
 
 
+def case_integrals():
+    """The setting of the reference's own test updes/tests/test_integrals.py (12x12 all-Dirichlet cloud, polyharmonic a = 5,
+    degree 3, s = x^2 / (1 + y^2)): get_field_coefficients, the field rebuilt with value_vec, integrate_field (pi/12 to 1e-1)."""
+    cloud = updes.SquareCloud(Nx=12, Ny=12, facet_types={"North": "d", "South": "d", "East": "d", "West": "d"}, support_size="max", noise_key=None)
+    rbf = partial(updes.polyharmonic, a=5)
+    xy = cloud.sorted_nodes
+    s = xy[:, 0] ** 2 / (1 + xy[:, 1] ** 2)
+    coeffs = updes.get_field_coefficients(s, cloud, rbf, 3)
+    rebuilt = updes.value_vec(cloud.sorted_nodes, coeffs, cloud.sorted_nodes, rbf)
+    return dict(cloud_arrays(cloud), s=npa(s), coeffs=npa(coeffs), rebuilt=npa(rebuilt),
+                integral=np.array(float(updes.integrate_field(coeffs, cloud, rbf, 3))))
+
+
 def case_config2(nb_steps=3):
     """Config 2 as the reference's demo defines it: constants, cloud (35x35, doubly periodic, key = None), operators and
     initial field are the source text of demos/Advection/01_adv_diff_periodic.py:34-93 executed unchanged; the time loop
@@ -413,7 +427,7 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
+         "ref_integrals_12x12": case_integrals, "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
 
 
 def main():

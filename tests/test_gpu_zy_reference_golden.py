@@ -319,3 +319,20 @@ def test_darcy_demo_against_the_unmodified_reference_script():
     rhs = np.concatenate([np.ones(cloud.Ni), np.zeros(cloud.N - cloud.Ni), np.zeros(6)])
     exact, _ = exact_solution(Kd, rhs, K[:cloud.N])
     assert np.max(np.abs(sol.vals - exact)) <= 1e-8 * np.max(np.abs(exact)) and backward_error(Kd, sol.coeffs, rhs) <= 1e-13
+
+
+def test_reference_test_integrals_on_the_product():
+    """updes/tests/test_integrals.py on the product: coefficients of s = x^2 / (1 + y^2) on a 12x12 cloud (polyharmonic a = 5,
+    degree 3; cond(A) = 2e12), the field rebuilt with value_vec, and integrate_field ~ pi/12 (the reference asserts 1e-1)."""
+    g = rc.load("ref_integrals_12x12")
+    cloud = u.SquareCloud(Nx=12, Ny=12, facet_types={"North": "d", "South": "d", "East": "d", "West": "d"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    rbf = partial(u.polyharmonic, a=5)
+    # the same coefficients through the CUDA evaluator: the reference's number
+    assert np.isclose(u.integrate_field(g["coeffs"], cloud, rbf, 3), float(g["integral"]), rtol=1e-8)
+    # the whole pipeline: the coefficients differ (cond 2e12) but the rebuilt field and the integral do not
+    coeffs = u.get_field_coefficients(g["s"], cloud, rbf, 3)
+    rebuilt = u.value_vec(cloud.sorted_nodes, coeffs, cloud.sorted_nodes, rbf)
+    assert np.mean(np.abs(rebuilt - g["s"])) <= 1e-6
+    val = u.integrate_field(coeffs, cloud, rbf, 3)
+    assert abs(val - np.pi / 12) < 1e-1 and abs(val - float(g["integral"])) <= 1e-4 * abs(float(g["integral"]))

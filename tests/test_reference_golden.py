@@ -443,3 +443,23 @@ def test_oracle_matches_the_unmodified_darcy_demo(oracle):
     k = g["perm_vals"][:Ni]
     coef2 = np.stack([np.zeros(Ni), np.zeros(Ni), np.zeros(Ni), -k, -k], axis=1)
     check("thin_plate", 3, coef2, oracle.assemble_q(cloud, np.ones(Ni), zero_bc), g["u_vals"], "Darcy solution")
+
+
+def test_integrate_field_host_logic_matches_the_reference(oracle, monkeypatch):
+    """integrate_field (operators.py:381-451; the function behind the reference's test_integrals.py): the product's point
+    sets and weights against the number the reference returned for the same coefficients.  The evaluator is replaced by
+    the oracle's here (host logic only; the GPU test uses the real one)."""
+    from updes_b200 import operators as ops
+    g = rc.load("ref_integrals_12x12")
+    cloud = u.SquareCloud(Nx=12, Ny=12, facet_types={"North": "d", "South": "d", "East": "d", "West": "d"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    monkeypatch.setattr(ops, "value", lambda x, cf, centers, rbf=None, clip_val=None: oracle.eval_field(
+        np.asarray(x, dtype=float).reshape(-1, 2), np.asarray(centers), np.ascontiguousarray(cf), "polyharmonic", 5, "value"))
+    val = ops.integrate_field(g["coeffs"], cloud, rc.kernel_rbf(u, "polyharmonic", 5), 3)
+    assert np.isclose(val, float(g["integral"]), rtol=1e-12)
+    assert abs(float(g["integral"]) - np.pi / 12) < 1e-1                                   # test_integrals.py:83-84
+    with pytest.raises(AssertionError):
+        ops.integrate_field(g["coeffs"], object(), u.polyharmonic, 3)
+    # the oracle agrees on the rebuilt field too (value_vec at the nodes from the reference's coefficients)
+    rebuilt = oracle.eval_field(cloud.sorted_nodes, cloud.sorted_nodes, g["coeffs"], "polyharmonic", 5, "value")
+    assert np.max(np.abs(rebuilt - g["rebuilt"])) <= 1e-9 * max(1.0, np.max(np.abs(g["rebuilt"])))

@@ -516,6 +516,32 @@ laplacian_vec = laplacian
 divergence_vec = divergence
 
 
+def integrate_field(field, cloud, rbf, max_degree):
+    """Integral over the unit square of a field given by its COEFFICIENTS, by the reference's weighted sum of evaluator
+    values (operators.py:381-451): weight 1 on an (Nx-1) x (Ny-1) set of interior points, 1/2 on edge points, 1/4 on
+    corners, times the cell area.  Restated as written, including how the reference builds its point sets -- the interior
+    points come from ``array(meshgrid(qx, qy)).reshape(nb_squares, 2)`` (a reshape of the stacked coordinate grids, not a
+    pairing of them) and the top-left corner re-uses the bottom-right point -- because its own known-answer test
+    (updes/tests/test_integrals.py:83, pi/12 to 1e-1) is defined on exactly this sum.  One batched evaluator call."""
+    if not (hasattr(cloud, "Nx") and hasattr(cloud, "Ny")):
+        raise AssertionError("The cloud must be a SquareCloud instance")
+    Nx, Ny = cloud.Nx, cloud.Ny
+    nb_squares = (Nx - 1) * (Ny - 1)
+    area = (1 / (Nx - 1)) * (1 / (Ny - 1))
+    qx = np.linspace(1 / (Nx - 1), 1 - 1 / (Nx - 1), Nx - 1)
+    qy = np.linspace(1 / (Ny - 1), 1 - 1 / (Ny - 1), Ny - 1)
+    inner = np.array(np.meshgrid(qx, qy)).reshape(nb_squares, 2)
+    ey = np.linspace(1 / (Ny - 1), 1 - 1 / (Ny - 1), Ny - 2)
+    ex = np.linspace(1 / (Nx - 1), 1 - 1 / (Nx - 1), Nx - 2)
+    left, right = np.stack((np.zeros(Ny - 2), ey), axis=-1), np.stack((np.ones(Ny - 2), ey), axis=-1)
+    bottom, top = np.stack((ex, np.zeros(Nx - 2)), axis=-1), np.stack((ex, np.ones(Nx - 2)), axis=-1)
+    corners = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 0.0], [1.0, 1.0]])        # bl, br, "tl" (= br in the reference), tr
+    pts = np.concatenate([inner, left, right, bottom, top, corners], axis=0)
+    w = np.concatenate([np.ones(nb_squares), np.full(2 * (Ny - 2) + 2 * (Nx - 2), 0.5), np.full(4, 0.25)])
+    vals = np.asarray(value(pts, field, cloud.sorted_nodes, rbf), dtype=np.float64)
+    return float(np.dot(w, vals) * area)
+
+
 def interpolate_field(field, cloud1, cloud2):
     """Carry a nodal field from ``cloud1`` to ``cloud2``: the same nodes, numbered differently because the
     boundary types differ (reference operators.py:457-480; a permutation, no arithmetic).  Used by the
