@@ -1,0 +1,54 @@
+"""The host layer and the `-m gpu` tests themselves, dry-run on a CPU emulation of the C-ABI (no GPU in the build
+container).  tests/cpu_abi_emulation.py replaces every libupdes_b200.so entry point by numpy / LAPACK with the header's
+semantics; the runners execute the GPU test files unchanged on it, in subprocesses (the emulation monkey-patches torch
+and must not leak into this process).  This proves the orchestration around the kernels and the tests' own logic --
+golden keys, tolerances, launch-count assertions, world-size > 1 drivers under gloo -- not the kernels: those are
+checked on a B200 by `pytest -m gpu`."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, *args, timeout=900):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], cwd=ROOT, capture_output=True,
+                       text=True, timeout=timeout)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return p.stdout
+
+
+def test_emulation_closed_forms_agree_with_the_oracle(oracle):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_abi_emulation as emu                # importing does not install anything
+    assert emu.self_check() <= 1e-13
+    # and the emulated assembly reproduces the oracle's K on a cloud with every row type but periodic
+    import updes_b200 as u
+    from updes_b200 import assembly as asm
+    cloud = u.SquareCloud(Nx=9, Ny=8, facet_types={"South": "n", "West": "d", "North": "r", "East": "d"})
+    rng = np.random.default_rng(1)
+    coef, betas = rng.normal(size=(cloud.Ni, 5)), rng.normal(size=cloud.Nr)
+    t = asm.build_operator_rows(cloud, coef, betas=betas)
+    lib = emu.EmulatedLib()
+    N, M = cloud.N, 6
+    ld = asm.padded_ld(N + M)
+    out = np.full((N + M, ld), np.nan)
+    ctr = np.ascontiguousarray(cloud.sorted_nodes)
+    keep = [np.ascontiguousarray(getattr(t, k)) for k in ("p1", "p2", "cphi1", "cphi2", "cpol1", "cpol2", "skip")]
+    from updes_b200._lib import UpdesRows
+    st = UpdesRows(ctr.ctypes.data, *[a.ctypes.data for a in keep])
+    assert lib.updes_assemble_rows(3, 1.5, N, M, ctr.ctypes.data, st, 0, N + M, 7, out.ctypes.data, ld, None) == 0
+    Kref = oracle.assemble_K(cloud, "multiquadric", 1.5, M, coef, betas)
+    assert np.max(np.abs(out[:, :N + M] - Kref)) <= 1e-12 * np.max(np.abs(Kref)) and not out[:, N + M:].any()
+
+
+def test_single_gpu_test_files_and_smoke_on_the_emulated_abi():
+    out = _run("run_gpu_tests_on_cpu.py")
+    assert "smoke ok" in out and " passed" in out and "failed" not in out
+
+
+def test_multi_gpu_test_files_on_the_emulated_abi_under_gloo():
+    out = _run("run_multi_gpu_tests_on_cpu.py", "--quick")
+    assert "hold on the emulated ABI + gloo" in out
