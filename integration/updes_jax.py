@@ -1,5 +1,6 @@
-"""jax.ffi wrappers over integration/updes_jax_ffi.cc -- SOURCE ONLY (JAX is not installed here, so this
-module has never been imported; everything it calls below the FFI line is exercised by tests/ through ctypes).
+"""jax.ffi wrappers over integration/updes_jax_ffi.cc.  JAX is not installed in this environment: the module is
+exercised by tests/run_jax_adapter.py over a jax.ffi stand-in and a mock of XLA's FFI binding API (tests/mock_xla),
+not against a real jaxlib.
 
 Drop into the reference as ``updes/b200.py``.  ``pde_solver`` keeps the reference's signature and result
 (updes/operators.py:559-618: ``SteadySol(vals, coeffs, mat)``) while assembly, the dense solve and the field
@@ -13,6 +14,7 @@ evaluation run in libupdes_b200.so on XLA-owned device buffers and the XLA strea
     sol_vals                                                 UpdesEvalJets: vals = [Phi P] c, matrix-free
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -26,7 +28,7 @@ from updes_b200.rbf import RBF_CODES, compute_nb_monomials, identify_rbf
 
 jax.config.update("jax_enable_x64", True)                                 # updes/config.py:15-16
 
-_so = ctypes.cdll.LoadLibrary("libupdes_jax_ffi.so")
+_so = ctypes.cdll.LoadLibrary(os.environ.get("UPDES_JAX_FFI_LIB", "libupdes_jax_ffi.so"))
 for _name in ("UpdesAssemble", "UpdesFactorSolve", "UpdesEvalJets"):
     jax.ffi.register_ffi_target(_name, jax.ffi.pycapsule(getattr(_so, _name)), platform="CUDA")
 _so.UpdesEvalJetsWorkspaceBytes.restype = ctypes.c_size_t
@@ -38,8 +40,9 @@ def assemble_K(cloud, table, kind, param, M):
     n = cloud.N + M
     mi, mb = table.masks()
     call = jax.ffi.ffi_call("UpdesAssemble", jax.ShapeDtypeStruct((n, padded_ld(n)), jnp.float64))
-    return call(jnp.asarray(cloud.sorted_nodes), jnp.asarray(table.p1), jnp.asarray(table.p2), jnp.asarray(table.cphi1),
-                jnp.asarray(table.cphi2), jnp.asarray(table.cpol1), jnp.asarray(table.cpol2), jnp.asarray(table.skip),
+    i32 = lambda a: jnp.asarray(a, dtype=jnp.int32)
+    return call(jnp.asarray(cloud.sorted_nodes), i32(table.p1), i32(table.p2), jnp.asarray(table.cphi1),
+                jnp.asarray(table.cphi2), jnp.asarray(table.cpol1), jnp.asarray(table.cpol2), i32(table.skip),
                 kind=np.int32(RBF_CODES[kind]), param=np.float64(param), M=np.int32(M), mask_internal=np.int32(mi),
                 mask_boundary=np.int32(mb), Ni=np.int32(cloud.Ni))
 

@@ -1,5 +1,6 @@
-// XLA FFI handlers over libupdes_b200.so -- SOURCE ONLY: not compiled in this environment (no jaxlib /
-// XLA FFI headers here).  See integration/README.md for the build line and INTEGRATION.md for context.
+// XLA FFI handlers over libupdes_b200.so.  No jaxlib / XLA FFI headers exist in this environment: the file is compiled
+// and run by the tests against a mock of the binding API (tests/mock_xla/xla/ffi/api/ffi.h), not against real XLA.
+// See integration/README.md for the build line and INTEGRATION.md for context.
 // Replaces, on the reference side: assemble_op_Phi_P / assemble_bd_Phi_P / assemble_A block assembly
 // (updes/assembly.py:10-362), inv + GEMM + lineax QR (updes/assembly.py:87-90,:398-401,
 // updes/operators.py:612-616) and the field evaluators (updes/operators.py:118-351).

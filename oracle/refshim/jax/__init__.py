@@ -8,6 +8,7 @@ from torch import func as _tf
 
 from . import numpy  # noqa: F401  (jax.numpy)
 from . import tree_util, lax, random  # noqa: F401
+from . import ffi  # noqa: F401  (custom-call surface used by integration/updes_jax.py)
 
 _F64 = torch.float64
 
@@ -18,6 +19,11 @@ class _Config:
 
 
 config = _Config()
+
+
+class ShapeDtypeStruct:
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(int(s) for s in shape), dtype
 
 
 def jit(fun=None, **kwargs):

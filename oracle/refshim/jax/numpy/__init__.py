@@ -9,6 +9,7 @@ newaxis = None
 inf = math.inf
 pi = math.pi
 _F64, _I64 = torch.float64, torch.int64
+float64, int64, int32 = torch.float64, torch.int64, torch.int32
 
 
 def _dtype(dt):

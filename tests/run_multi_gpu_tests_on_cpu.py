@@ -6,7 +6,7 @@ and the public API on the sharded path.  Each spawned rank installs the emulatio
 host drivers and the test logic at world sizes the build container has no GPUs for -- not the kernels.
 
     python tests/run_multi_gpu_tests_on_cpu.py            # every parametrisation, world <= 4
-    python tests/run_multi_gpu_tests_on_cpu.py --quick    # first parametrisation of each test only
+    python tests/run_multi_gpu_tests_on_cpu.py --quick    # smallest case of the three world-size > 1 drivers only
 """
 import importlib
 import os
@@ -18,6 +18,9 @@ from pathlib import Path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+QUICK = ("test_block_cyclic_lu_world2", "test_public_api_on_the_sharded_path", "test_grid2d_2x2")
 
 
 def _emulated(rank, module, fn_name, args):
@@ -46,6 +49,8 @@ def main():
     for modname in ("test_gpu_distributed", "test_gpu_zx_grid2d"):
         mod = importlib.import_module(modname)
         for name in sorted(n for n in dir(mod) if n.startswith("test_")):
+            if "--quick" in sys.argv and name not in QUICK:
+                continue
             fn = getattr(mod, name)
             params = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
             cases = params[0].args[1] if params else [()]

@@ -52,3 +52,11 @@ def test_single_gpu_test_files_and_smoke_on_the_emulated_abi():
 def test_multi_gpu_test_files_on_the_emulated_abi_under_gloo():
     out = _run("run_multi_gpu_tests_on_cpu.py", "--quick")
     assert "hold on the emulated ABI + gloo" in out
+
+
+def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emulated_abi():
+    """integration/updes_jax_ffi.cc compiled against tests/mock_xla (the Bind() chains must match the handlers'
+    signatures) with its updes_* calls forwarded to the emulation; integration/updes_jax.py over the jax.ffi stand-in:
+    its pde_solver equals the product's and the reference's own result."""
+    out = _run("run_jax_adapter.py", "--emulated", timeout=600)
+    assert "jax.ffi adapter ok (emulated C-ABI, CPU)" in out
