@@ -592,3 +592,24 @@ def test_symbolic_and_numeric_lowering_agree_on_random_linear_operators():
         want = np.stack([w[k, 0] + w[k, 1] * xs + w[k, 2] * F[trial % 3, :Ni] for k in range(5)], axis=1)
         assert np.allclose(a, want, rtol=1e-14, atol=1e-15) and np.allclose(b, want, rtol=1e-14, atol=1e-15)
         assert np.array_equal(a, ap) and np.array_equal(b, bp)
+
+
+def test_robin_betas_follow_the_reference_offset_rule_when_facets_interleave():
+    """Q8 (operators.py:535-536): betas[i - node_ids[0]] with the jax out-of-bounds clamp.  North owns the corners, so
+    with East also Robin its last node is numbered after East's nodes: offset > len - 1 -> the last beta."""
+    import warnings
+    cloud = u.SquareCloud(Nx=5, Ny=4, facet_types={"South": "d", "West": "d", "North": "r", "East": "r"})
+    north, east = cloud.facet_nodes["North"], cloud.facet_nodes["East"]
+    assert north[-1] - north[0] > len(north) - 1 and east[-1] - east[0] == len(east) - 1      # North interleaved, East contiguous
+    bn, be = np.arange(10.0, 10.0 + len(north)), np.arange(20.0, 20.0 + len(east))
+    bcs = {"South": 0.0, "West": 0.0, "North": (np.zeros(len(north)), bn), "East": (np.zeros(len(east)), be)}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        robin, new_bc = u.duplicate_robin_coeffs(bcs, cloud)
+    assert any("not numbered contiguously" in str(m.message) for m in w)
+    for k, i in enumerate(east):
+        assert robin[i] == be[k]
+    for i in north:
+        assert robin[i] == bn[min(i - north[0], len(north) - 1)]
+    assert robin[north[-1]] == bn[-1] and set(robin) == set(north) | set(east)
+    assert new_bc["North"] is bcs["North"][0] and new_bc["South"] == 0.0

@@ -60,3 +60,8 @@ def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emula
     its pde_solver equals the product's and the reference's own result."""
     out = _run("run_jax_adapter.py", "--emulated", timeout=600)
     assert "jax.ffi adapter ok (emulated C-ABI, CPU)" in out
+
+
+def test_randomised_solves_of_the_host_layer_against_oracle_assembled_systems():
+    out = _run("run_solver_fuzz_on_cpu.py", "7", "12", timeout=600)
+    assert "0 outside the bounds" in out

@@ -576,8 +576,16 @@ def duplicate_robin_coeffs(boundary_conditions, cloud):
                 # the reference calls warning.warn on an un-imported name here and dies with
                 # AttributeError (operators.py:1,:530); keep it an explicit error
                 raise ValueError("Robin facet %r needs a (value, beta) tuple" % f_id)
+            # operators.py:535-536 indexes betas with i - node_ids[0] ("TODO: this assumes consistent ordering"): when two
+            # Robin facets interleave in the renumbering (North / South own the corners, so their last node comes after
+            # the East / West nodes) the offset runs past the end, and a jax array then returns its LAST element
+            # (out-of-bounds gathers clamp).  Kept as the reference computes it (quirk Q8).
+            last = len(node_ids) - 1
+            if node_ids and node_ids[-1] - node_ids[0] > last:
+                warnings.warn("Robin facet %r: its nodes are not numbered contiguously (another Robin facet interleaves); "
+                              "betas are assigned by offset from the first node, clamped, as the reference does" % f_id)
             for i in node_ids:
-                robin_coeffs[i] = betas[i - node_ids[0]]          # operators.py:535-536 (contiguous ids)
+                robin_coeffs[i] = betas[min(i - node_ids[0], last)]
         else:
             new_bc[f_id] = boundary_conditions[f_id]
     return robin_coeffs, new_bc
