@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-QUICK = ("test_block_cyclic_lu_world2", "test_public_api_on_the_sharded_path", "test_grid2d_2x2")
+QUICK = ("test_block_cyclic_lu_world2", "test_sharded_api_with_nodal_fields", "test_grid2d_2x2")
 
 
 def _emulated(rank, module, fn_name, args):
@@ -46,7 +46,7 @@ def main():
 
     mp.spawn = spawn
     ran = 0
-    for modname in ("test_gpu_distributed", "test_gpu_zx_grid2d"):
+    for modname in ("test_gpu_distributed", "test_gpu_zx_grid2d", "test_gpu_zz_sharded_api_fields"):
         mod = importlib.import_module(modname)
         for name in sorted(n for n in dir(mod) if n.startswith("test_")):
             if "--quick" in sys.argv and name not in QUICK:
