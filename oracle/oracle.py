@@ -375,6 +375,19 @@ def assemble_op_Phi_P(cloud, kind, param, M, rowcoef):
     return opPhi, opP
 
 
+def op_rows(cloud, kind, param, M, rows, rowcoef):
+    """assembly.py:126-135 for a list of internal rows (full-size checks): (len(rows), N) and (len(rows), M)."""
+    nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    rowcoef = np.ascontiguousarray(rowcoef, dtype=np.float64)
+    assert rowcoef.shape == (len(rows), 5) and (rows < cloud.Ni).all()
+    opPhi = np.zeros((len(rows), cloud.N))
+    opP = np.zeros((len(rows), M))
+    lib().uo_op_rows(_dp(nodes), ctypes.c_int(cloud.N), ctypes.c_int(M), ctypes.c_int(RBF_KINDS[kind]), ctypes.c_double(param),
+                     _ip(rows), ctypes.c_int(len(rows)), _dp(rowcoef), _dp(opPhi), _dp(opP))
+    return opPhi, opP
+
+
 def assemble_bd_Phi_P(cloud, kind, param, M, betas=None):
     """assembly.py:141-362"""
     nodes = np.ascontiguousarray(cloud.sorted_nodes, dtype=np.float64)

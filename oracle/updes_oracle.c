@@ -191,6 +191,30 @@ void uo_assemble_op_Phi_P(const double *nodes, int N, int Ni, int M, int kind, d
 }
 
 /*
+ * The same rows (assembly.py:126-135) for a LIST of internal row indices: what full-size parity checks use, where the
+ * whole Ni x N block does not fit on the host.  opPhi is nrows x N, opP nrows x M; rowcoef is nrows x 5 (of the listed rows).
+ */
+void uo_op_rows(const double *nodes, int N, int M, int kind, double param, const int *rows, int nrows,
+                const double *rowcoef, double *opPhi, double *opP)
+{
+    double jet[5];
+    memset(opPhi, 0, sizeof(double) * (size_t)nrows * N);
+    for (int t = 0; t < nrows; t++) {
+        const int i = rows[t];
+        const double *c = rowcoef + 5 * (size_t)t;
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;                      /* support excludes self */
+            uo_rbf_jet(kind, param, nodes[2 * i], nodes[2 * i + 1], nodes[2 * j], nodes[2 * j + 1], jet);
+            opPhi[(size_t)t * N + j] = dot5(c, jet);
+        }
+        for (int j = 0; j < M; j++) {
+            uo_monomial_jet(j, nodes[2 * i], nodes[2 * i + 1], jet);
+            opP[(size_t)t * M + j] = dot5(c, jet);
+        }
+    }
+}
+
+/*
  * assembly.py:141-362 -- boundary rows, in the order d, n, r, periodic-value rows of every
  * periodic group, periodic-flux rows of every group.
  *   normals : sorted_outward_normals, (Nn + Nr + sum(Np)) x 2, indexed [i - Ni - Nd]

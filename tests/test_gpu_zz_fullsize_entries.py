@@ -1,0 +1,61 @@
+"""Entry-wise parity at the headline size as SURVEY.md section 8(d) words it: ">= 10^6 random (i, j) + all boundary rows against
+the closed-form oracle" -- 300 x 300 = 90 000 nodes, n = 90 003 (BASELINE.json configs[3]).  The whole matrix cannot be
+rebuilt on the host, but whole ROWS can: ALL 1 196 boundary rows (the oracle's own `assemble_bd_Phi_P`, 1.08e8 entries),
+12 random internal rows (`uo_op_rows`: assembly.py:126-135 for a row list, 1.08e6 entries) and the P^T rows, for the
+headline Laplace operator (the kernel's closed-form radial-Laplacian path) and for an advection-diffusion operator with
+per-row coefficients (the general-jet path of configs 2 / 3).  Bit-for-bit zero where the reference leaves zeros (own
+column, padding).  UPDES_FULLSIZE_NX shrinks the cloud for the dry run on the emulated C-ABI (tests/run_gpu_tests_on_cpu.py);
+written after the round's GPU minutes were spent, hence late in file order."""
+import os
+
+import numpy as np
+import pytest
+
+import updes_b200 as u
+from updes_b200 import assembly as asm
+from helpers import CONFIG1_FACETS, rel_err_rowscaled, true_rel_err
+
+pytestmark = pytest.mark.gpu
+NX = int(os.environ.get("UPDES_FULLSIZE_NX", "300"))
+
+
+@pytest.mark.parametrize("operator", ["laplace", "advection_diffusion"])
+def test_all_boundary_rows_and_a_million_internal_entries_at_the_headline_size(oracle, operator):
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 8.5 * (NX * NX + 3) ** 2:
+        pytest.skip("needs ~66 GB of free HBM")
+    cloud = u.SquareCloud(Nx=NX, Ny=NX, facet_types=CONFIG1_FACETS)
+    N, Ni, M = cloud.N, cloud.Ni, 3
+    n = N + M
+    xy = cloud.sorted_nodes
+    if operator == "laplace":
+        coef = np.tile([0.0, 0, 0, 1.0, 1.0], (Ni, 1))
+    else:       # u/DT + (vx(x) d/dx + vy(x) d/dy) u - k lap(u), velocities varying from row to row
+        coef = np.stack([np.full(Ni, 1e4), 100.0 * np.cos(3 * xy[:Ni, 1]), 50.0 * np.sin(2 * xy[:Ni, 0]), np.full(Ni, -0.08), np.full(Ni, -0.08)], axis=1)
+    rows = asm.DeviceRows(cloud, asm.build_operator_rows(cloud, coef))
+    K = asm.assemble_system(rows, "polyharmonic", 1.0, M)
+    assert K.shape[0] == n and torch.all(K[:, n:] == 0)
+    rng = np.random.default_rng(11)
+    pick = np.sort(rng.choice(Ni, size=12, replace=False)).astype(np.int32)
+    # internal rows
+    opPhi, opP = oracle.op_rows(cloud, "polyharmonic", 1.0, M, pick, coef[pick])
+    want = np.concatenate([opPhi, opP], axis=1)
+    got = K[torch.as_tensor(pick.astype(np.int64)).cuda(), :n].cpu().numpy()
+    e_int, t_int = rel_err_rowscaled(got, want), true_rel_err(got, want)
+    assert np.all(got[np.arange(12), pick] == 0.0), "own column must stay exactly 0 (Q1)"
+    # every boundary row
+    bdPhi, bdP = oracle.assemble_bd_Phi_P(cloud, "polyharmonic", 1.0, M)
+    want = np.concatenate([bdPhi, bdP], axis=1)
+    got = K[Ni:N, :n].cpu().numpy()
+    e_bd, t_bd = rel_err_rowscaled(got, want), true_rel_err(got, want)
+    assert np.all(got[np.arange(N - Ni), np.arange(Ni, N)] == 0.0)
+    del bdPhi, want, got
+    # P^T rows
+    P = oracle.assemble_P(cloud, M)
+    got = K[N:, :n].cpu().numpy()
+    assert np.max(np.abs(got[:, :N] - P.T)) <= 1e-15 and not got[:, N:].any()
+    print("%s, n = %d: %d internal entries row-scaled %.2e (true per-entry %.2e); %d boundary entries row-scaled %.2e (true %.2e)"
+          % (operator, n, 12 * n, e_int, t_int, (N - Ni) * n, e_bd, t_bd))
+    assert e_int <= 1e-12 and e_bd <= 1e-12            # north_star: assembled entries within 1e-12 relative
+    assert t_int <= 2e-10 and t_bd <= 2e-10            # entries above 1e-6 of their row's scale: true relative error

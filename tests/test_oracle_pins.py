@@ -224,3 +224,16 @@ def test_closed_form_jets_match_50_digit_differentiation(oracle, kind, param):
                 worst_true = max(worst_true, abs(g - w) / abs(w))
     assert worst_scaled <= 1e-13, (kind, param, worst_scaled)
     assert worst_true <= 2e-10, (kind, param, worst_true)      # entries down to 1e-6 of the jet scale keep >= 4 extra digits
+
+
+def test_op_rows_equals_the_rows_of_the_full_block(oracle):
+    """uo_op_rows (row-list form used by the full-size GPU parity test) == the same rows of uo_assemble_op_Phi_P."""
+    import updes_b200 as u
+    cloud = u.SquareCloud(Nx=9, Ny=7, facet_types={"South": "n", "West": "d", "North": "r", "East": "d"})
+    rng = np.random.default_rng(5)
+    coef = rng.normal(size=(cloud.Ni, 5))
+    for kind, param in (("polyharmonic", 1.0), ("gaussian", 2.0), ("thin_plate", 2.0)):
+        full_phi, full_p = oracle.assemble_op_Phi_P(cloud, kind, param, 6, coef)
+        pick = np.array([0, 3, cloud.Ni - 1, 17], dtype=np.int32)
+        phi, p = oracle.op_rows(cloud, kind, param, 6, pick, coef[pick])
+        assert np.array_equal(phi, full_phi[pick]) and np.array_equal(p, full_p[pick])
