@@ -22,6 +22,7 @@ NX = int(os.environ.get("UPDES_FULLSIZE_NX", "300"))
 @pytest.mark.parametrize("operator", ["laplace", "advection_diffusion"])
 def test_all_boundary_rows_and_a_million_internal_entries_at_the_headline_size(oracle, operator):
     import torch
+    u.clear_cache()                                    # drops cached factorisations of earlier tests and empties torch's cache
     free, _ = torch.cuda.mem_get_info()
     if free < 8.5 * (NX * NX + 3) ** 2:
         pytest.skip("needs ~66 GB of free HBM")
