@@ -446,6 +446,9 @@ def install():
     if _installed is not None:
         return _installed
     import torch
+    if torch.cuda.is_available():
+        raise RuntimeError("cpu_abi_emulation: a CUDA device is present -- the emulation exists for GPU-less containers only "
+                           "and must never stand in for libupdes_b200.so where the real path can run")
     from updes_b200 import _lib
     emu = EmulatedLib()
     _lib.load = lambda: emu

@@ -9,8 +9,12 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the emulation refuses to install where a GPU exists (there the real `-m gpu` suite is the check)
+needs_no_gpu = pytest.mark.skipif(torch.cuda.is_available(), reason="a CUDA device is present: run pytest -m gpu instead")
 
 
 def _run(script, *args, timeout=900):
@@ -44,16 +48,19 @@ def test_emulation_closed_forms_agree_with_the_oracle(oracle):
     assert np.max(np.abs(out[:, :N + M] - Kref)) <= 1e-12 * np.max(np.abs(Kref)) and not out[:, N + M:].any()
 
 
+@needs_no_gpu
 def test_single_gpu_test_files_and_smoke_on_the_emulated_abi():
     out = _run("run_gpu_tests_on_cpu.py")
     assert "smoke ok" in out and " passed" in out and "failed" not in out
 
 
+@needs_no_gpu
 def test_multi_gpu_test_files_on_the_emulated_abi_under_gloo():
     out = _run("run_multi_gpu_tests_on_cpu.py", "--quick")
     assert "hold on the emulated ABI + gloo" in out
 
 
+@needs_no_gpu
 def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emulated_abi():
     """integration/updes_jax_ffi.cc compiled against tests/mock_xla (the Bind() chains must match the handlers'
     signatures) with its updes_* calls forwarded to the emulation; integration/updes_jax.py over the jax.ffi stand-in:
@@ -62,6 +69,7 @@ def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emula
     assert "jax.ffi adapter ok (emulated C-ABI, CPU)" in out
 
 
+@needs_no_gpu
 def test_randomised_solves_of_the_host_layer_against_oracle_assembled_systems():
     out = _run("run_solver_fuzz_on_cpu.py", "7", "12", timeout=600)
     assert "0 outside the bounds" in out
