@@ -246,7 +246,7 @@ def test_cache_evicts_least_recently_used_before_building(monkeypatch):
     """room for a new system is made BEFORE it is built, by evicting least-recently-used factorisations until
     the prediction fits the budget; a cached left-hand side costs two sweeps, an evicted one a new factorisation."""
     from updes_b200 import _lib, operators as ops
-    cloud = u.SquareCloud(Nx=20, Ny=16, facet_types=CONFIG1_FACETS)
+    cloud = u.SquareCloud(Nx=32, Ny=26, facet_types=CONFIG1_FACETS)
     one = ops._System.predict_nbytes(cloud.N + 3)
     monkeypatch.setattr(ops, "cache_budget_bytes", lambda: int(2.5 * one))
     zero = lambda c: 0.0
