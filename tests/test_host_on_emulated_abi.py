@@ -4,6 +4,7 @@ semantics; the runners execute the GPU test files unchanged on it, in subprocess
 and must not leak into this process).  This proves the orchestration around the kernels and the tests' own logic --
 golden keys, tolerances, launch-count assertions, world-size > 1 drivers under gloo -- not the kernels: those are
 checked on a B200 by `pytest -m gpu`."""
+import atexit
 import os
 import subprocess
 import sys
@@ -17,11 +18,38 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 needs_no_gpu = pytest.mark.skipif(torch.cuda.is_available(), reason="a CUDA device is present: run pytest -m gpu instead")
 
 
-def _run(script, *args, timeout=900):
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], cwd=ROOT, capture_output=True,
-                       text=True, timeout=timeout)
-    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    return p.stdout
+JOBS = {                    # the four dry runs are independent processes: started together, collected one per test
+    "single": ("run_gpu_tests_on_cpu.py",),
+    "multi": ("run_multi_gpu_tests_on_cpu.py", "--quick"),
+    "jax": ("run_jax_adapter.py", "--emulated"),
+    "fuzz": ("run_solver_fuzz_on_cpu.py", "7", "12"),
+}
+_procs = {}
+
+
+def _reap():
+    for p in _procs.values():
+        if p.poll() is None:
+            p.kill()
+
+
+atexit.register(_reap)
+
+
+def _run(job, timeout=900):
+    if not _procs:
+        env = dict(os.environ, OMP_NUM_THREADS="2")
+        for name, cmd in JOBS.items():
+            _procs[name] = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", cmd[0]), *cmd[1:]], cwd=ROOT, env=env,
+                                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = _procs[job]
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    assert p.returncode == 0, out[-3000:] + err[-3000:]
+    return out
 
 
 def test_emulation_closed_forms_agree_with_the_oracle(oracle):
@@ -50,13 +78,13 @@ def test_emulation_closed_forms_agree_with_the_oracle(oracle):
 
 @needs_no_gpu
 def test_single_gpu_test_files_and_smoke_on_the_emulated_abi():
-    out = _run("run_gpu_tests_on_cpu.py")
+    out = _run("single")
     assert "smoke ok" in out and " passed" in out and "failed" not in out
 
 
 @needs_no_gpu
 def test_multi_gpu_test_files_on_the_emulated_abi_under_gloo():
-    out = _run("run_multi_gpu_tests_on_cpu.py", "--quick")
+    out = _run("multi")
     assert "hold on the emulated ABI + gloo" in out
 
 
@@ -65,11 +93,11 @@ def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emula
     """integration/updes_jax_ffi.cc compiled against tests/mock_xla (the Bind() chains must match the handlers'
     signatures) with its updes_* calls forwarded to the emulation; integration/updes_jax.py over the jax.ffi stand-in:
     its pde_solver equals the product's and the reference's own result."""
-    out = _run("run_jax_adapter.py", "--emulated", timeout=600)
+    out = _run("jax")
     assert "jax.ffi adapter ok (emulated C-ABI, CPU)" in out
 
 
 @needs_no_gpu
 def test_randomised_solves_of_the_host_layer_against_oracle_assembled_systems():
-    out = _run("run_solver_fuzz_on_cpu.py", "7", "12", timeout=600)
+    out = _run("fuzz")
     assert "0 outside the bounds" in out
