@@ -463,3 +463,29 @@ def test_integrate_field_host_logic_matches_the_reference(oracle, monkeypatch):
     # the oracle agrees on the rebuilt field too (value_vec at the nodes from the reference's coefficients)
     rebuilt = oracle.eval_field(cloud.sorted_nodes, cloud.sorted_nodes, g["coeffs"], "polyharmonic", 5, "value")
     assert np.max(np.abs(rebuilt - g["rebuilt"])) <= 1e-9 * max(1.0, np.max(np.abs(g["rebuilt"])))
+
+
+@pytest.mark.parametrize("name,args", [
+    ("ref_laplace_12x9", dict(Nx=12, Ny=9, facet_types={"South": "n", "West": "d", "North": "d", "East": "d"})),
+    ("ref_periodic_10x10", dict(Nx=10, Ny=10, facet_types={"South": "p1", "North": "p1", "West": "p2", "East": "p2"})),
+    ("ref_robin_11x8", None)])
+def test_lazy_local_supports_have_the_reference_neighbour_order_up_to_ties(name, args):
+    """cloud.local_supports[i] (reference cloud.py:83-112; read by demos/Advection/00_...:68): computed per access instead of
+    stored as an (N, N-1) table.  Against the first rows of the reference's own table: the same nodes, self excluded, at the
+    same sequence of distances; equidistant nodes may come in another order (BallTree's there, by id here)."""
+    g = rc.load(name)
+    cloud = u.SquareCloud(**(args if args is not None else rc.robin(u).cloud_args))
+    ref = g["supports_first_rows"]
+    ls = cloud.local_supports
+    assert len(ls) == cloud.N and list(ls.keys()) == list(range(cloud.N)) and (cloud.N - 1) in ls and cloud.N not in ls
+    xy = cloud.sorted_nodes
+    for i in range(ref.shape[0]):
+        ours = np.array(ls[i])
+        assert ours.shape == (cloud.N - 1,) and i not in ours and sorted(ours) == sorted(ref[i])
+        dist = lambda idx: np.linalg.norm(xy[idx] - xy[i], axis=1)
+        assert np.all(np.diff(dist(ours)) >= -1e-15)
+        assert np.allclose(dist(ours), dist(ref[i]), rtol=0, atol=1e-14)
+    table = cloud.sorted_local_supports
+    assert table.shape == (cloud.N, cloud.N - 1) and np.array_equal(table[2], np.array(ls[2]))
+    with pytest.raises(KeyError):
+        ls[cloud.N]

@@ -21,6 +21,41 @@ import os
 import numpy as np
 
 
+class _LazySupports:
+    """Read-only mapping node id -> list of the other nodes by increasing distance (ties by id), computed per access."""
+
+    def __init__(self, nodes):
+        self._nodes = nodes
+
+    def __len__(self):
+        return self._nodes.shape[0]
+
+    def __iter__(self):
+        return iter(range(len(self)))
+
+    def keys(self):
+        return range(len(self))
+
+    def __contains__(self, i):
+        return isinstance(i, (int, np.integer)) and 0 <= i < len(self)
+
+    def __getitem__(self, i):
+        n = len(self)
+        i = int(i)
+        if not 0 <= i < n:
+            raise KeyError(i)
+        d = self._nodes - self._nodes[i]
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+        order = np.lexsort((np.arange(n), d2))
+        return [int(j) for j in order if j != i]
+
+    def items(self):
+        return ((i, self[i]) for i in range(len(self)))
+
+    def values(self):
+        return (self[i] for i in range(len(self)))
+
+
 class Cloud:
     """Base bookkeeping shared by all clouds (reference cloud.py:10-50)."""
 
@@ -117,6 +152,23 @@ class Cloud:
     def nodes(self):
         """dict new id -> coordinates (reference attribute ``Cloud.nodes`` after renumbering)."""
         return {i: self.sorted_nodes[i] for i in range(self.N)}
+
+    @property
+    def local_supports(self):
+        """``cloud.local_supports[i]``: the other N - 1 nodes ordered by distance from node i (reference cloud.py:83-112 with
+        ``support_size="max"``; demos read it to pick a node's neighbourhood, e.g. demos/Advection/00_...:68).  The reference
+        stores all N lists; here a list is computed when it is asked for (O(N log N) each), so a 250k-node cloud does not
+        carry an (N, N - 1) table.  Equidistant nodes are ordered by node id (the reference takes BallTree's order there,
+        which is implementation-defined)."""
+        return _LazySupports(self.sorted_nodes)
+
+    @property
+    def sorted_local_supports(self):
+        """(N, N - 1) int array of the lists above (cloud.py:403-408).  Small clouds only."""
+        if self.N > 20000:
+            raise MemoryError("sorted_local_supports is an (N, N-1) table; the global path never needs it (N = %d)" % self.N)
+        ls = self.local_supports
+        return np.array([ls[i] for i in range(self.N)], dtype=np.int64).reshape(self.N, max(self.N - 1, 0))
 
     def sort_dict_by_keys(self, dictionary):
         """cloud.py:72-81"""
