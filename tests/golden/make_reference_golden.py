@@ -26,6 +26,8 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_laplace_demo_30x30  demos/Laplace/00_laplace_with_rbf.py run unmodified as a whole script: solution, Laplacian at the nodes, its printed errors
   ref_darcy_demo_20x20    demos/Darcy/00_darcy_flow.py run unmodified: identity-operator solve (polyharmonic a=2) and -div(k grad u) = 1 (thin_plate a=3)
   ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
+  ref_advection00_2steps  demos/Advection/00_advection_with_rbf.py: its definitions (40x20, d/d/d/n, u0 from cloud.local_supports), two steps
+  ref_advection02_sink_2steps  demos/Advection/02_adv_diff_periodic_with_sink.py: its definitions (sink field through diff_args), two steps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
@@ -405,6 +407,47 @@ def case_config2(nb_steps=3):
                 max_degree=np.array(ns["MAX_DEGREE"]), coeffs_last=npa(ufield.coeffs))
 
 
+def _advection_demo(relpath, nb_steps, with_sink):
+    """Constants, cloud, operators and initial field = the demo's source text executed unchanged (up to its time loop);
+    the loop below is the demo's own pde_solver_jit call, run for `nb_steps` of its steps."""
+    import jax
+    src = open(os.path.join(REFERENCE, relpath)).read()
+    body = src[src.index("RBF = partial(polyharmonic, a=1)"):src.index("## Begin timestepping for 100 steps")]
+    ns = {k: getattr(updes, k) for k in dir(updes) if not k.startswith("_")}
+    ns.update(jax=jax, jnp=jnp, partial=partial, key=None)
+    exec(compile(body, os.path.basename(relpath), "exec"), ns)
+    cloud, u = ns["cloud"], ns["u0"]
+    ulist = [npa(u)]
+    for _ in range(nb_steps):
+        kw = dict(diff_args=[ns["u_sink"]]) if with_sink else {}
+        ufield = updes.pde_solver_jit(diff_operator=ns["my_diff_operator"], rhs_operator=ns["my_rhs_operator"], rhs_args=[u],
+                                      cloud=cloud, boundary_conditions=ns["boundary_conditions"], rbf=ns["RBF"],
+                                      max_degree=ns["MAX_DEGREE"], **kw)
+        u = ufield.vals
+        ulist.append(npa(u))
+    out = dict(cloud_arrays(cloud), u=np.stack(ulist), DT=np.array(ns["DT"]), K=np.array(ns["K"]), VEL=npa(ns["VEL"]),
+               max_degree=np.array(ns["MAX_DEGREE"]), coeffs_last=npa(ufield.coeffs))
+    return out, ns, cloud
+
+
+def case_advection00(nb_steps=2):
+    """demos/Advection/00_advection_with_rbf.py (40x20, Dirichlet on three sides, Neumann outflow, degree 1): its u0 is
+    0.95 on the N // 40 nearest neighbours of one node, read from cloud.local_supports (:66-69)."""
+    out, ns, cloud = _advection_demo("demos/Advection/00_advection_with_rbf.py", nb_steps, False)
+    sid = int(ns["source_id"])
+    out.update(source_id=np.array(sid), source_neighbors=npa(ns["source_neighbors"]).astype(np.int64),
+               source_support=np.array(cloud.local_supports[sid], dtype=np.int64))
+    return out
+
+
+def case_advection02(nb_steps=2):
+    """demos/Advection/02_adv_diff_periodic_with_sink.py (35x35 doubly periodic, pure advection K = 0, VEL = 500, degree 0):
+    the operator carries a nodal sink field through diff_args (`fields[0] * val`, :58-62)."""
+    out, ns, _ = _advection_demo("demos/Advection/02_adv_diff_periodic_with_sink.py", nb_steps, True)
+    out.update(u_sink=npa(ns["u_sink"]))
+    return out
+
+
 def case_config3(nb_iter=2):
     """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
     is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
@@ -427,7 +470,8 @@ def case_config3(nb_iter=2):
 CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case_robin, "ref_periodic_10x10": case_periodic,
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
-         "ref_integrals_12x12": case_integrals, "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh}
+         "ref_integrals_12x12": case_integrals, "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh,
+         "ref_advection00_2steps": case_advection00, "ref_advection02_sink_2steps": case_advection02}
 
 
 def main():

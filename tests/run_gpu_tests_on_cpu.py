@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # files whose tests go through the emulated entry points only (whole-matrix LU, assembly, evaluators);
 # test_gpu_lu.py / test_gpu_distributed.py / test_gpu_zx_grid2d.py drive kernel building blocks that are not emulated
-DEFAULT = ["tests/test_gpu_solver.py", "tests/test_gpu_assembly.py", "tests/test_gpu_zy_reference_golden.py", "tests/test_gpu_zz_cache_lru.py",
+DEFAULT = ["tests/test_gpu_solver.py", "tests/test_gpu_assembly.py", "tests/test_gpu_zy_reference_golden.py", "tests/test_gpu_zz_cache_lru.py", "tests/test_gpu_zz_advection_demos.py",
            "tests/test_gpu_zz_fullsize_entries.py"]          # (the last one at 40 x 40 instead of 300 x 300)
 
 

@@ -1,0 +1,79 @@
+"""Two more callers of the hot path, as the reference's demos define them (golden vectors: the demos' own definitions
+executed from their source by tests/golden/make_reference_golden.py, two steps of their own pde_solver_jit loop):
+demos/Advection/00_advection_with_rbf.py (Dirichlet + Neumann outflow, u0 picked through cloud.local_supports) and
+demos/Advection/02_adv_diff_periodic_with_sink.py (nodal sink field through diff_args on the doubly periodic cloud).
+Every step is taken from the REFERENCE's previous field and compared with the reference's next field (north_star: 1e-8).
+Written after the round's GPU minutes were spent: dry-run on the emulated C-ABI, late in file order."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+import updes_b200 as u
+import reference_cases as rc
+
+pytestmark = pytest.mark.gpu
+
+
+def _steps(g, cloud, op, rhs, diff_args=None):
+    from updes_b200 import _lib
+    bcs = {k: (lambda p: 0.0) for k in cloud.facet_types}
+    rbf = partial(u.polyharmonic, a=1)
+    u.clear_cache()
+    worst = 0.0
+    for s in range(g["u"].shape[0] - 1):
+        _lib.profile_enable(True)
+        sol = u.pde_solver_jit(diff_operator=op, rhs_operator=rhs, diff_args=diff_args, rhs_args=[g["u"][s]], cloud=cloud,
+                               boundary_conditions=bcs, rbf=rbf, max_degree=int(g["max_degree"]))
+        worst = max(worst, float(np.max(np.abs(sol.vals - g["u"][s + 1])) / np.max(np.abs(g["u"][s + 1]))))
+        if s > 0:            # unchanged left-hand side: no assembly, no factorisation after the first step
+            assert _lib.profile_read("gemm")[2] == 0 and _lib.profile_read("panel")[2] == 0 and _lib.profile_read("assemble")[2] == 0
+    _lib.profile_enable(False)
+    u.clear_cache()
+    return worst
+
+
+def test_advection_demo_with_outflow_against_the_reference():
+    g = rc.load("ref_advection00_2steps")
+    cloud = u.SquareCloud(Nx=40, Ny=20, facet_types={"South": "d", "West": "d", "North": "d", "East": "n"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    DT, K, VEL = float(g["DT"]), float(g["K"]), g["VEL"]
+    RBF = partial(u.polyharmonic, a=1)
+
+    def op(x, center=None, rbf=None, monomial=None, fields=None):
+        val = u.nodal_value(x, center, rbf, monomial)
+        grad = u.nodal_gradient(x, center, rbf, monomial)
+        lap = u.nodal_laplacian(x, center, rbf, monomial)
+        return (val / DT) + u.dot(VEL, grad) - K * lap
+
+    rhs = lambda x, centers=None, rbf=None, fields=None: u.value(x, fields[:, 0], centers, RBF) / DT      # (the demo passes its global RBF)
+    # the demo's initial field, built the demo's way: 0.95 on the N // 40 nearest neighbours of node int(0.01 N)
+    source_id = int(cloud.N * 0.01)
+    nb = np.array(cloud.local_supports[source_id][:cloud.N // 40])
+    xy = cloud.sorted_nodes
+    far = lambda idx: np.linalg.norm(xy[idx] - xy[source_id], axis=1)
+    rest = np.array(cloud.local_supports[source_id][cloud.N // 40:cloud.N // 40 + 1])
+    if far(nb[-1:])[0] < far(rest)[0] - 1e-12:       # no tie at the cut: the same 20 nodes as the reference picked
+        u0 = np.zeros(cloud.N); u0[nb] = 0.95
+        assert np.array_equal(u0, g["u"][0])
+    d = _steps(g, cloud, op, rhs)
+    print("Advection/00 demo: product-vs-reference %.2e" % d)
+    assert d <= 1e-8
+
+
+def test_advection_demo_with_a_sink_field_against_the_reference():
+    g = rc.load("ref_advection02_sink_2steps")
+    cloud = u.SquareCloud(Nx=35, Ny=35, facet_types={"South": "p1", "North": "p1", "West": "p2", "East": "p2"})
+    rc.assert_cloud_equals_golden(cloud, g)
+    DT, K, VEL = float(g["DT"]), float(g["K"]), g["VEL"]
+
+    def op(x, center=None, rbf=None, monomial=None, fields=None):
+        val = u.nodal_value(x, center, rbf, monomial)
+        grad = u.nodal_gradient(x, center, rbf, monomial)
+        lap = u.nodal_laplacian(x, center, rbf, monomial)
+        return (val / DT) + u.dot(VEL, grad) - K * lap + fields[0] * val
+
+    rhs = lambda x, centers=None, rbf=None, fields=None: u.value(x, fields[:, 0], centers, rbf) / DT
+    d = _steps(g, cloud, op, rhs, diff_args=[g["u_sink"]])
+    print("Advection/02 demo: product-vs-reference %.2e" % d)
+    assert d <= 1e-8

@@ -489,3 +489,57 @@ def test_lazy_local_supports_have_the_reference_neighbour_order_up_to_ties(name,
     assert table.shape == (cloud.N, cloud.N - 1) and np.array_equal(table[2], np.array(ls[2]))
     with pytest.raises(KeyError):
         ls[cloud.N]
+
+
+ADV00_FACETS = {"South": "d", "West": "d", "North": "d", "East": "n"}
+ADV02_FACETS = {"South": "p1", "North": "p1", "West": "p2", "East": "p2"}
+
+
+def _oracle_advection_steps(oracle, g, cloud, M, sink=None):
+    """One implicit step per golden step, restated on the oracle from the REFERENCE's previous field: coefficients of the
+    previous field through A, value(x)/DT on internal nodes, reference formulation of the solve."""
+    DT, K, VEL = float(g["DT"]), float(g["K"]), g["VEL"]
+    Ni, xy = cloud.Ni, cloud.sorted_nodes
+    c0 = np.full(Ni, 1 / DT) + (0.0 if sink is None else sink[:Ni])
+    coef = np.stack([c0, np.full(Ni, VEL[0]), np.full(Ni, VEL[1]), np.full(Ni, -K), np.full(Ni, -K)], axis=1)
+    A = oracle.assemble_A(cloud, "polyharmonic", 1, M)
+    zero_bc = {k: np.zeros(len(cloud.facet_nodes[k])) for k in cloud.facet_types}
+    worst = 0.0
+    for s in range(g["u"].shape[0] - 1):
+        cprev = np.linalg.solve(A, np.concatenate([g["u"][s], np.zeros(M)]))
+        q_int = oracle.eval_field(xy[:Ni], xy, cprev, "polyharmonic", 1, "value") / DT
+        vals, _, _ = oracle.reference_solve(cloud, "polyharmonic", 1, int(g["max_degree"]), coef, oracle.assemble_q(cloud, q_int, zero_bc))
+        worst = max(worst, float(np.max(np.abs(vals - g["u"][s + 1])) / np.max(np.abs(g["u"][s + 1]))))
+    return worst
+
+
+def test_oracle_matches_the_advection_demo_with_outflow(oracle):
+    """demos/Advection/00_advection_with_rbf.py (definitions executed from its source by the generator): 40x20, Dirichlet on
+    three sides and a Neumann outflow, degree 1, u0 = 0.95 on the 20 nearest neighbours of node 8 read from
+    cloud.local_supports; two implicit steps."""
+    g = rc.load("ref_advection00_2steps")
+    cloud = oracle.RefSquareCloud(40, 20, ADV00_FACETS)
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert int(g["max_degree"]) == 1 and int(g["source_id"]) == 8 and len(g["source_neighbors"]) == 20
+    u0 = np.zeros(cloud.N); u0[g["source_neighbors"]] = 0.95
+    assert np.array_equal(g["u"][0], u0)
+    assert _oracle_advection_steps(oracle, g, cloud, 3) <= 1e-8
+    # the product's per-access supports give the demo the same neighbourhood: the same 20 nodes unless the 20th and 21st
+    # neighbours are equidistant (ties are ordered by BallTree in the reference), and always the same distances
+    pc = u.SquareCloud(Nx=40, Ny=20, facet_types=ADV00_FACETS)
+    ours = np.array(pc.local_supports[8])
+    xy = pc.sorted_nodes
+    dist = lambda idx: np.linalg.norm(xy[idx] - xy[8], axis=1)
+    assert np.allclose(dist(ours), dist(g["source_support"]), rtol=0, atol=1e-14)
+    if dist(ours[19:20])[0] < dist(ours[20:21])[0] - 1e-12:
+        assert set(ours[:20].tolist()) == set(g["source_neighbors"].tolist())
+
+
+def test_oracle_matches_the_advection_demo_with_a_sink_field(oracle):
+    """demos/Advection/02_adv_diff_periodic_with_sink.py: pure advection (K = 0, VEL = 500) on the doubly periodic 35x35
+    cloud, degree 0, the operator's `fields[0] * val` term fed by a nodal sink field through diff_args; two steps."""
+    g = rc.load("ref_advection02_sink_2steps")
+    cloud = oracle.RefSquareCloud(35, 35, ADV02_FACETS)
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert float(g["K"]) == 0.0 and int(g["max_degree"]) == 0 and g["u_sink"].shape == (cloud.N,)
+    assert _oracle_advection_steps(oracle, g, cloud, 1, sink=g["u_sink"]) <= 1e-8
