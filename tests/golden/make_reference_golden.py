@@ -28,6 +28,8 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_config2_advdiff_3steps  config 2: the Advection demo's own definitions (35x35 periodic cloud, operators, u0), three time steps
   ref_advection00_2steps  demos/Advection/00_advection_with_rbf.py: its definitions (40x20, d/d/d/n, u0 from cloud.local_supports), two steps
   ref_advection02_sink_2steps  demos/Advection/02_adv_diff_periodic_with_sink.py: its definitions (sink field through diff_args), two steps
+  ref_grayscott001_2steps demos/Gray-Scott/001_gray-scott.py: periodic ids 'p0' / 'p1' with degree 1, two steps
+  ref_wave00_2steps       demos/Wave/00_wave.py: all-Neumann cloud, polyharmonic a=3, degree 2, two nodal fields in the rhs, two steps
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
@@ -448,6 +450,37 @@ def case_advection02(nb_steps=2):
     return out
 
 
+def case_grayscott001(nb_steps=2):
+    """demos/Gray-Scott/001_gray-scott.py (despite its name an advection-diffusion loop): 40x20 cloud with periodic ids
+    "p0" / "p1", degree 1 (three monomials beside periodic rows), u0 through cloud.local_supports of the middle node."""
+    out, ns, cloud = _advection_demo("demos/Gray-Scott/001_gray-scott.py", nb_steps, False)
+    sid = int(ns["source_id"])
+    out.update(source_id=np.array(sid), source_neighbors=npa(ns["source_neighbors"]).astype(np.int64),
+               source_support=np.array(cloud.local_supports[sid], dtype=np.int64))
+    return out
+
+
+def case_wave00(nb_steps=2):
+    """demos/Wave/00_wave.py: all four facets Neumann (no Dirichlet row at all), polyharmonic a = 3, degree 2, operator
+    val / DT^2 + C lap, right-hand side from TWO nodal fields (2 u_prev - u_prev_prev) / DT^2; definitions executed from the
+    demo's source, the loop below is its own (:88-100), two of its 500 steps."""
+    import jax
+    src = open(os.path.join(REFERENCE, "demos/Wave/00_wave.py")).read()
+    body = src[src.index("RBF = partial(polyharmonic, a=3)"):src.index("## Begin timestepping for 100 steps")]
+    ns = {k: getattr(updes, k) for k in dir(updes) if not k.startswith("_")}
+    ns.update(jax=jax, jnp=jnp, partial=partial, key=None)
+    exec(compile(body, "00_wave.py", "exec"), ns)
+    cloud, u0, DT = ns["cloud"], ns["u0"], ns["DT"]
+    ulist = [u0, 1 * DT + u0]
+    for _ in range(nb_steps):
+        ufield = updes.pde_solver_jit(diff_operator=ns["my_diff_operator"], rhs_operator=ns["my_rhs_operator"],
+                                      rhs_args=[ulist[-1], ulist[-2]], cloud=cloud, boundary_conditions=ns["boundary_conditions"],
+                                      rbf=ns["RBF"], max_degree=ns["MAX_DEGREE"])
+        ulist.append(ufield.vals)
+    return dict(cloud_arrays(cloud), u=np.stack([npa(x) for x in ulist]), DT=np.array(DT), C=np.array(ns["C"]),
+                max_degree=np.array(ns["MAX_DEGREE"]), coeffs_last=npa(ufield.coeffs))
+
+
 def case_config3(nb_iter=2):
     """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
     is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
@@ -471,7 +504,8 @@ CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case
          "ref_kernels_7x6": case_kernels, "ref_config1_30x20": lambda: case_laplace(30, 20, keep_blocks=False),
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
          "ref_integrals_12x12": case_integrals, "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh,
-         "ref_advection00_2steps": case_advection00, "ref_advection02_sink_2steps": case_advection02}
+         "ref_advection00_2steps": case_advection00, "ref_advection02_sink_2steps": case_advection02,
+         "ref_grayscott001_2steps": case_grayscott001, "ref_wave00_2steps": case_wave00}
 
 
 def main():

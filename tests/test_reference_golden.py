@@ -543,3 +543,63 @@ def test_oracle_matches_the_advection_demo_with_a_sink_field(oracle):
     rc.assert_cloud_equals_golden(cloud, g)
     assert float(g["K"]) == 0.0 and int(g["max_degree"]) == 0 and g["u_sink"].shape == (cloud.N,)
     assert _oracle_advection_steps(oracle, g, cloud, 1, sink=g["u_sink"]) <= 1e-8
+
+
+GS_FACETS = {"South": "p0", "North": "p0", "West": "p1", "East": "p1"}
+ALL_NEUMANN = {"South": "n", "North": "n", "West": "n", "East": "n"}
+
+
+def test_oracle_matches_the_gray_scott_demo_periodic_ids_with_degree_one(oracle):
+    """demos/Gray-Scott/001_gray-scott.py: periodic ids "p0" / "p1" (suffixed "p00", "p01", "p12", "p13" by facet position),
+    three monomial columns beside the periodic rows, u0 through cloud.local_supports; two implicit steps."""
+    g = rc.load("ref_grayscott001_2steps")
+    cloud = oracle.RefSquareCloud(40, 20, GS_FACETS)
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert [str(t) for t in g["facet_types"]] == ["p00", "p01", "p12", "p13"] and int(g["max_degree"]) == 1
+    assert _oracle_advection_steps(oracle, g, cloud, 3) <= 1e-8
+    pc = u.SquareCloud(Nx=40, Ny=20, facet_types=GS_FACETS)
+    rc.assert_cloud_equals_golden(pc, g)
+    sid = int(g["source_id"])
+    xy = pc.sorted_nodes
+    dist = lambda idx: np.linalg.norm(xy[idx] - xy[sid], axis=1)
+    assert np.allclose(dist(np.array(pc.local_supports[sid])), dist(g["source_support"]), rtol=0, atol=1e-14)
+
+
+def wave_exact_steps(oracle, g, cloud):
+    """For every golden step of the wave demo: (exact next field, oracle's next field).  'Exact' = the discrete step solved
+    with extended-precision refinement throughout (coefficients of the two previous fields through A, then K), from the
+    REFERENCE's previous fields.  cond(A) = 2e12 and cond(K) = 2e17 (rows of size 1/DT^2 = 4e6 beside rows of size 1) here,
+    so the inverse-based pipelines -- the reference's and the oracle's -- each sit ~5e-6 from it."""
+    DT, C, M = float(g["DT"]), float(g["C"]), 6
+    Ni, N, xy = cloud.Ni, cloud.N, cloud.sorted_nodes
+    coef = np.tile([1 / DT ** 2, 0.0, 0.0, C, C], (Ni, 1))
+    A = oracle.assemble_A(cloud, "polyharmonic", 3, M)
+    K = oracle.assemble_K(cloud, "polyharmonic", 3, M, coef)
+    zero_bc = {k: np.zeros(len(cloud.facet_nodes[k])) for k in cloud.facet_types}
+    val = lambda c: oracle.eval_field(xy[:Ni], xy, c, "polyharmonic", 3, "value")
+    out = []
+    for s in range(1, g["u"].shape[0] - 1):
+        cx = [exact_solution(A, np.concatenate([g["u"][t], np.zeros(M)]), A[:N])[1] for t in (s, s - 1)]
+        q = oracle.assemble_q(cloud, (2 * val(cx[0]) - val(cx[1])) / DT ** 2, zero_bc)
+        exact, _ = exact_solution(K, np.concatenate([q, np.zeros(M)]), A[:N])
+        cn = [np.linalg.solve(A, np.concatenate([g["u"][t], np.zeros(M)])) for t in (s, s - 1)]
+        qn = oracle.assemble_q(cloud, (2 * val(cn[0]) - val(cn[1])) / DT ** 2, zero_bc)
+        vals, _, _ = oracle.reference_solve(cloud, "polyharmonic", 3, 2, coef, qn)
+        out.append((exact, vals))
+    return out
+
+
+def test_oracle_matches_the_wave_demo_all_neumann_two_fields(oracle):
+    """demos/Wave/00_wave.py: no Dirichlet row at all (four Neumann facets), polyharmonic a = 3, degree 2, the right-hand side
+    evaluates two nodal fields; two steps, each restated from the reference's two previous fields.  Agreement is asserted to
+    the accuracy the inverse-based pipelines have on this system (see wave_exact_steps)."""
+    g = rc.load("ref_wave00_2steps")
+    cloud = oracle.RefSquareCloud(25, 25, ALL_NEUMANN)
+    rc.assert_cloud_equals_golden(cloud, g)
+    assert cloud.Nd == 0 and cloud.Nn == 96 and int(g["max_degree"]) == 2 and g["u"].shape[0] == 4
+    for s, (exact, vals) in enumerate(wave_exact_steps(oracle, g, cloud), start=1):
+        sc = np.max(np.abs(exact))
+        e_gold, e_ours, d = (np.max(np.abs(g["u"][s + 1] - exact)) / sc, np.max(np.abs(vals - exact)) / sc,
+                             np.max(np.abs(vals - g["u"][s + 1])) / sc)
+        print("wave demo step %d: reference-vs-exact %.2e, oracle-vs-exact %.2e, oracle-vs-reference %.2e" % (s, e_gold, e_ours, d))
+        assert d <= max(1e-8, 4.0 * e_gold) and e_ours <= max(1e-8, 4.0 * e_gold)
