@@ -4,6 +4,7 @@ tests themselves in a container without a GPU (tests/cpu_abi_emulation.py says w
 
     python tests/run_gpu_tests_on_cpu.py                      # the default file list below + smoke()
     python tests/run_gpu_tests_on_cpu.py tests/test_gpu_solver.py -k coupled
+    python tests/run_gpu_tests_on_cpu.py --smoke tests/test_gpu_zy_reference_golden.py      # listed files, then smoke()
 
 Not collected by pytest (no test_ prefix); tests/test_host_on_emulated_abi.py runs a bounded subset of it in a subprocess.
 """
@@ -25,9 +26,11 @@ def main(argv):
     import cpu_abi_emulation as emu
     emu.install()
     import pytest
+    smoke = not argv or "--smoke" in argv
+    argv = [a for a in argv if a != "--smoke"]
     args = argv or DEFAULT
     rc = pytest.main(["-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + [os.path.join(ROOT, a) if a.startswith("tests/") else a for a in args])
-    if not argv and rc == 0:
+    if smoke and rc == 0:
         import __graft_entry__ as g
         g.smoke()
     return int(rc)
