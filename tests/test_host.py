@@ -613,3 +613,23 @@ def test_robin_betas_follow_the_reference_offset_rule_when_facets_interleave():
         assert robin[i] == bn[min(i - north[0], len(north) - 1)]
     assert robin[north[-1]] == bn[-1] and set(robin) == set(north) | set(east)
     assert new_bc["North"] is bcs["North"][0] and new_bc["South"] == 0.0
+
+
+def test_star_import_gives_a_reference_script_the_names_it_takes_from_updes():
+    """The reference's demos start with `from updes import *` and use, beside the solver surface, names that updes/utils.py
+    merely imports (partial, Partial, os) and its small helpers (plot, dataloader, make_dir, RK4 ...)."""
+    ns = {}
+    exec("from updes_b200 import *", ns)
+    for name in ("SquareCloud", "GmshCloud", "pde_solver", "pde_solver_jit", "pde_multi_solver", "polyharmonic", "gaussian",
+                 "nodal_value", "nodal_gradient", "nodal_laplacian", "nodal_div_grad", "value", "gradient", "laplacian",
+                 "divergence", "gradient_vec", "interpolate_field", "integrate_field", "get_field_coefficients",
+                 "partial", "Partial", "os", "make_dir", "random_name", "RK4", "plot", "dataloader"):
+        assert name in ns, name
+    assert ns["partial"](ns["polyharmonic"], a=2).keywords == {"a": 2} and ns["Partial"] is ns["partial"]
+    data = np.arange(20).reshape(10, 2)
+    batches = list(u.dataloader(data, 3, 5))
+    assert [b.shape for b in batches] == [(3, 2)] * 3                         # `while end < dataset_size`: 3, 6, 9 -- never the rest
+    rows = np.concatenate(batches)
+    assert len({tuple(r) for r in rows}) == 9 and all(tuple(r) in {tuple(d) for d in data} for r in rows)
+    assert [b.tolist() for b in u.dataloader(data, 3, 5)] == [b.tolist() for b in batches]   # same key, same batches
+    assert list(u.dataloader(data, 10, 0)) == []

@@ -18,7 +18,12 @@ from .operators import (BatchPoints, OperatorLoweringError, SteadySol, assemble_
                         zerofy_periodic_cond)
 
 from .autodiff import linear_solve
-from .utils import RK4, dot_mat, dot_vec, make_dir, print_line_by_line, random_name
+from .utils import RK4, dataloader, dot_mat, dot_vec, make_dir, plot, print_line_by_line, random_name
+# the reference's demo scripts take these names from `from updes import *` (updes/utils.py imports them at module level);
+# Partial is jax.tree_util.Partial there -- a partial application, which is all the demos use it for
+import os  # noqa: E402,F401
+from functools import partial  # noqa: E402,F401
+from functools import partial as Partial  # noqa: E402,F401
 from .explicit import (assemble_A, assemble_B, assemble_P, assemble_Phi, assemble_bd_Phi_P, assemble_invert_A,
                        assemble_op_Phi_P)
 

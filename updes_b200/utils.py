@@ -61,3 +61,46 @@ def RK4(fun, t_span, y0, *args, t_eval=None, subdivisions=1, **kwargs):
         t_prev = t
         ys.append(y)
     return np.stack(ys)[np.arange(0, t_solve.size, subdivisions)]
+
+
+def plot(*args, ax=None, figsize=(6, 3.5), x_label=None, y_label=None, title=None, x_scale="linear", y_scale="linear",
+         xlim=None, ylim=None, **kwargs):
+    """Line plot on a (new) matplotlib axis (utils.py:164-185).  Needs matplotlib, which the solver itself does not."""
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError as e:
+        raise ImportError("updes_b200.plot needs matplotlib, which is not installed; the solver itself does not") from e
+    if ax is None:
+        _, ax = plt.subplots(1, 1, figsize=figsize)
+    if x_label:
+        ax.set_xlabel(x_label)
+    if y_label:
+        ax.set_ylabel(y_label)
+    if title:
+        ax.set_title(title)
+    ax.plot(*args, **kwargs)
+    ax.set_xscale(x_scale)
+    ax.set_yscale(y_scale)
+    if "label" in kwargs:
+        ax.legend()
+    if ylim:
+        ax.set_ylim(ylim)
+    if xlim:
+        ax.set_xlim(xlim)
+    plt.tight_layout()
+    return ax
+
+
+def dataloader(array, batch_size, key):
+    """Shuffled mini-batches of the rows of ``array`` (utils.py:188-197): a permutation drawn from ``key`` (an integer seed
+    or a numpy Generator here; a jax PRNG key in the reference, whose random stream cannot be reproduced without JAX), then
+    consecutive slices of it while a whole batch BEFORE the end of the data remains -- the reference's loop condition
+    ``end < dataset_size``, which never yields the last batch."""
+    array = np.asarray(array)
+    n = array.shape[0]
+    rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
+    perm = rng.permutation(n)
+    start, end = 0, batch_size
+    while end < n:
+        yield array[perm[start:end]]
+        start, end = end, end + batch_size
