@@ -510,7 +510,7 @@ def test_explicit_assembly_names_exist_and_refuse_large_clouds():
 
 
 def test_cloud_plotting_helpers_of_the_reference_surface():
-    """visualize_cloud / visualize_normals / visualize_field / average_spacing exist with the reference's signatures
+    """visualize_cloud / visualize_normals / visualize_field / animate_fields / average_spacing exist with the reference's signatures
     (cloud.py:62-70, :175-285; the README example ends with cloud.visualize_field(...)).  Host-only: without matplotlib
     they raise ImportError; with a pyplot module they draw (here: the no-op stand-in of oracle/refshim, in a subprocess)."""
     import importlib.util
@@ -529,6 +529,9 @@ def test_cloud_plotting_helpers_of_the_reference_surface():
             "c.visualize_cloud(s=6); c.visualize_normals()\n"
             "ax, img = c.visualize_field(np.arange(c.N, dtype=float), cmap='jet', projection='3d', title='RBF solution')\n"
             "ax, img = c.visualize_field(np.arange(c.N, dtype=float)[:, None], levels=20)\n"
+            "hist = [np.full(c.N, float(k)) for k in range(4)]\n"
+            "axes = c.animate_fields([hist, np.stack(hist)], cmaps='jet', filename='x.gif', titles=['a', 'b'], vmin=0, vmax=1)\n"
+            "assert len(axes) == 2 and len(c.animate_fields([hist], titles=['only'])) == 1\n"
             "print('drawn')\n" % (root, os.path.join(root, "oracle", "refshim")))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "drawn" in r.stdout, r.stderr[-1500:]

@@ -25,7 +25,9 @@ JOBS = {                    # the four dry runs are independent processes: start
     "multi": ("run_multi_gpu_tests_on_cpu.py", "--quick"),
     "jax": ("run_jax_adapter.py", "--emulated"),
     "fuzz": ("run_solver_fuzz_on_cpu.py", "7", "12"),
+    "demos": ("run_reference_demo_on_product.py",),
 }
+REFERENCE = "/root/reference"
 _procs = {}
 
 
@@ -42,6 +44,8 @@ def _run(job, timeout=900):
     if not _procs:
         env = dict(os.environ, OMP_NUM_THREADS="2")
         for name, cmd in JOBS.items():
+            if name == "demos" and not os.path.isdir(REFERENCE):
+                continue
             _procs[name] = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", cmd[0]), *cmd[1:]], cwd=ROOT, env=env,
                                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     p = _procs[job]
@@ -104,3 +108,14 @@ def test_jax_ffi_adapter_compiles_against_the_mock_xla_api_and_runs_on_the_emula
 def test_randomised_solves_of_the_host_layer_against_oracle_assembled_systems():
     out = _run("fuzz")
     assert "0 outside the bounds" in out
+
+
+@needs_no_gpu
+def test_reference_demo_scripts_run_unmodified_on_the_product():
+    """demos/Laplace/00_laplace_with_rbf.py and demos/Darcy/00_darcy_flow.py of the reference executed as they are, with
+    `updes` aliased to `updes_b200` (tests/run_reference_demo_on_product.py): same solution as the reference computed for
+    the same script (1.4e-10 / 1.4e-8), same error figure printed (4.559171e-07 vs 4.559172e-07)."""
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("needs /root/reference (build container)")
+    out = _run("demos")
+    assert "reference demos ran unmodified on the product" in out

@@ -24,6 +24,14 @@ from .utils import RK4, dataloader, dot_mat, dot_vec, make_dir, plot, print_line
 import os  # noqa: E402,F401
 from functools import partial  # noqa: E402,F401
 from functools import partial as Partial  # noqa: E402,F401
+try:                                        # plt / sns reach the demos through the star import too; both are optional here
+    import matplotlib.pyplot as plt  # noqa: E402,F401
+except ImportError:
+    pass
+try:
+    import seaborn as sns  # noqa: E402,F401
+except ImportError:
+    pass
 from .explicit import (assemble_A, assemble_B, assemble_P, assemble_Phi, assemble_bd_Phi_P, assemble_invert_A,
                        assemble_op_Phi_P)
 

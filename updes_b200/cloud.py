@@ -261,6 +261,50 @@ class Cloud:
         plt.tight_layout()
         return ax, img
 
+    def animate_fields(self, fields, filename=None, titles="Field", xlabel=r"$x$", ylabel=r"$y$", levels=50, figsize=(6, 5),
+                       cmaps="jet", cbarsplit=50, duration=5, colorbar=True, vmin=None, vmax=None, **kwargs):
+        """One filled-contour animation per field history, stacked vertically (reference surface, cloud.py:276-358; the
+        demos end with it).  ``fields``: list of histories, each a list of nodal fields or a (steps, N) array.  Saved with
+        pillow (.gif) or ffmpeg (.mp4) when ``filename`` is given; returns the axes.  Host-only, needs matplotlib."""
+        plt = self._pyplot()
+        from matplotlib.animation import FuncAnimation
+        histories = [np.stack([np.asarray(f, dtype=np.float64) for f in h], axis=0) if isinstance(h, (list, tuple))
+                     else np.asarray(h, dtype=np.float64) for h in fields]
+        x, y = np.asarray(self.sorted_nodes[:, 0]), np.asarray(self.sorted_nodes[:, 1])
+        fig, axes = plt.subplots(len(histories), 1, figsize=figsize, sharex=True)
+        axes = [axes] if len(histories) == 1 else list(axes)
+        cmaps = list(cmaps) if isinstance(cmaps, (list, tuple)) else [cmaps] * len(histories)
+        ranges = []
+        for k, (h, ax) in enumerate(zip(histories, axes)):
+            lo = float(np.min(h)) if vmin is None else vmin
+            hi = float(np.max(h)) if vmax is None else vmax
+            if hi <= lo:
+                hi = lo + 1e-3                                   # a constant history still needs a colour range
+            ranges.append((lo, hi))
+            ax.tricontourf(x, y, h[0], levels=levels, vmin=lo, vmax=hi, cmap=cmaps[k], **kwargs)
+            if colorbar:
+                mappable = plt.cm.ScalarMappable(cmap=cmaps[k])
+                mappable.set_array(h)
+                mappable.set_clim(lo, hi)
+                plt.colorbar(mappable, boundaries=np.linspace(lo, hi, cbarsplit), shrink=1.0, aspect=10, ax=ax)
+            ax.set_title(titles[k] if isinstance(titles, (list, tuple)) and k < len(titles) else
+                         (titles if isinstance(titles, str) and len(histories) == 1 else "field # %d" % (k + 1)))
+            if k == len(histories) - 1:
+                ax.set_xlabel(xlabel)
+            ax.set_ylabel(ylabel)
+
+        def draw(frame):
+            return [ax.tricontourf(x, y, h[frame], levels=levels, vmin=r[0], vmax=r[1], cmap=c, extend="min", **kwargs)
+                    for ax, h, r, c in zip(axes, histories, ranges, cmaps)]
+
+        steps = histories[0].shape[0]
+        anim = FuncAnimation(fig, draw, frames=steps, repeat=False, interval=100)
+        plt.tight_layout()
+        if filename:
+            anim.save(filename, writer="ffmpeg" if str(filename).endswith(".mp4") else "pillow", fps=steps / duration)
+            print("Animation saved at:", filename)
+        return axes
+
 
 class SquareCloud(Cloud):
     """Regular or jittered grid on the unit square (reference cloud.py:378-510).
