@@ -5,7 +5,7 @@ from the stand-ins of oracle/refshim (torch-backed arrays go in, the product con
 C-ABI is the CPU emulation of tests/cpu_abi_emulation.py (the build container has no GPU).  What the script computed is
 compared with what the REFERENCE computed for the same script (tests/golden/ref_*.npz).  Needs /root/reference.
 
-    python tests/run_reference_demo_on_product.py                 # Laplace/00 and Darcy/00 (seconds)
+    python tests/run_reference_demo_on_product.py                 # Laplace/00, Darcy/00, the NS/30 projection loop (seconds)
     python tests/run_reference_demo_on_product.py --all           # + the 100-step Advection / Gray-Scott loops (minutes on the emulation)
 """
 import os
@@ -64,6 +64,28 @@ def main():
     d1, d2 = rel(ns["perm_field"].vals, g["perm_vals"]), rel(ns["ufield"].vals, g["u_vals"])
     print("Darcy/00_darcy_flow.py: permeability solve vs the reference's %.2e, Darcy solution %.2e" % (d1, d2))
     assert d1 <= 2e-7 and d2 <= 2e-7            # both pipelines carry ~1e-8 at cond(K) = 3e11
+
+    # config 3: the projection loop of demos/NavierStokes/30_channel_flow_blowing_suction.py -- the script itself builds its
+    # clouds with the gmsh package, so (as the golden generator does with the reference) the source text of its operators
+    # and of simulate_forward_navier_stokes is executed unchanged, here against the product, on the reference's mesh.msh
+    import jax
+    import jax.numpy as jnp
+    from functools import partial
+    src = open(os.path.join(REFERENCE, "demos/NavierStokes/30_channel_flow_blowing_suction.py")).read()
+    body = src[src.index("def diff_operator_u("):src.index("def diff_operator_id(")]
+    ns = {k: getattr(updes_b200, k) for k in dir(updes_b200) if not k.startswith("_")}
+    ns.update(jax=jax, jnp=jnp, Partial=partial, partial=partial, RBF=updes_b200.polyharmonic, MAX_DEGREE=1, Re=100, Pa=0., NB_ITER=5)
+    exec(compile(body, "30_channel_flow_blowing_suction.py", "exec"), ns)
+    mesh = os.path.join(REFERENCE, "updes/tests/data/mesh.msh")
+    vel = {"Wall": "d", "Inflow": "d", "Outflow": "n", "Blowing": "d", "Suction": "d"}
+    phi = {"Wall": "n", "Inflow": "n", "Outflow": "d", "Blowing": "n", "Suction": "n"}
+    updes_b200.clear_cache()
+    u_list, v_list, _, p_list = ns["simulate_forward_navier_stokes"](updes_b200.GmshCloud(filename=mesh, facet_types=vel),
+                                                                     updes_b200.GmshCloud(filename=mesh, facet_types=phi), NB_ITER=2)
+    g = rc.load("ref_config3_ns_2iter")
+    d = max(rel(lst[k], g[name][k]) for name, lst in (("u", u_list), ("v", v_list), ("p", p_list)) for k in (1, 2))
+    print("NavierStokes/30 simulate_forward_navier_stokes (source unchanged, two iterations): u, v, p vs the reference's %.2e" % d)
+    assert d <= 2e-5                            # both pipelines feed inv(A)-level errors (cond 1e9) into the next solve
 
     if "--all" in sys.argv:
         for relpath, golden in (("Advection/00_advection_with_rbf.py", "ref_advection00_2steps"),
