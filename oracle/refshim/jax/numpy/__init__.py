@@ -94,18 +94,22 @@ def dot(a, b):
 
 
 def sum(x, axis=None):  # noqa: A001
+    x = array(x)
     return torch.sum(x) if axis is None else torch.sum(x, dim=axis)
 
 
 def mean(x, axis=None):
+    x = array(x)
     return torch.mean(x) if axis is None else torch.mean(x, dim=axis)
 
 
 def max(x, axis=None):  # noqa: A001
+    x = array(x)
     return torch.max(x) if axis is None else torch.max(x, dim=axis).values
 
 
 def min(x, axis=None):  # noqa: A001
+    x = array(x)
     return torch.min(x) if axis is None else torch.min(x, dim=axis).values
 
 
@@ -150,15 +154,15 @@ def where(cond, a, b):
 
 
 def trace(x):
-    return torch.trace(x)
+    return torch.trace(array(x))
 
 
 def clip(x, lo, hi):
-    return torch.clamp(x, lo, hi)
+    return torch.clamp(array(x), lo, hi)
 
 
 def flip(x, axis=0):
-    return torch.flip(x, dims=(axis,))
+    return torch.flip(array(x), dims=(axis,))
 
 
 def set_printoptions(**kw):
@@ -168,15 +172,16 @@ def set_printoptions(**kw):
 class linalg:
     @staticmethod
     def norm(x, axis=None):
+        x = array(x)                       # jnp functions accept numpy arrays too
         return torch.linalg.norm(x) if axis is None else torch.linalg.norm(x, dim=axis)
 
     @staticmethod
     def inv(a):
-        return torch.linalg.inv(a)          # LAPACK getrf + getri, as jaxlib's CPU path
+        return torch.linalg.inv(array(a))   # LAPACK getrf + getri, as jaxlib's CPU path
 
     @staticmethod
     def solve(a, b):
-        return torch.linalg.solve(a, b)
+        return torch.linalg.solve(array(a), array(b))
 
 
 class _At:

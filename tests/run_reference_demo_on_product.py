@@ -3,7 +3,8 @@
 `from updes import *` takes the product's surface), jax / jax.numpy / matplotlib / seaborn -- absent from the image -- come
 from the stand-ins of oracle/refshim (torch-backed arrays go in, the product converts them with numpy.asarray), and the
 C-ABI is the CPU emulation of tests/cpu_abi_emulation.py (the build container has no GPU).  What the script computed is
-compared with what the REFERENCE computed for the same script (tests/golden/ref_*.npz).  Needs /root/reference.
+compared with what the REFERENCE computed for the same script (tests/golden/ref_*.npz).  The reference's OWN three tests
+(updes/tests/test_*.py) are run the same way first.  Needs /root/reference.
 
     python tests/run_reference_demo_on_product.py                 # Laplace/00, Darcy/00, the NS/30 projection loop (seconds)
     python tests/run_reference_demo_on_product.py --all           # + the 100-step Advection / Gray-Scott loops (minutes on the emulation)
@@ -50,8 +51,33 @@ def rel(a, b):
     return float(np.max(np.abs(npa(a) - b)) / np.max(np.abs(b)))
 
 
+def reference_own_tests():
+    """updes/tests/test_{interpolation,integrals,operators}.py of the reference, unmodified, on the product: the files are
+    loaded under another module name (inside the reference tree pytest would import the `updes` package they sit in) and
+    every test_* function is called; they read "updes/tests/data/mesh.msh" relative to the reference's root."""
+    import importlib.util
+    cwd = os.getcwd()
+    os.chdir(REFERENCE)
+    ran = 0
+    try:
+        for name in ("test_interpolation", "test_integrals", "test_operators"):
+            updes_b200.clear_cache()
+            spec = importlib.util.spec_from_file_location("reference_" + name, os.path.join(REFERENCE, "updes", "tests", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            for fn in sorted(n for n in dir(mod) if n.startswith("test_") and callable(getattr(mod, n))):
+                getattr(mod, fn)()
+                ran += 1
+                print("passed on the product: updes/tests/%s.py::%s" % (name, fn), flush=True)
+    finally:
+        os.chdir(cwd)
+    assert ran == 3
+    print("the reference's own %d tests pass on the product" % ran)
+
+
 def main():
     assert os.path.isdir(REFERENCE), "needs /root/reference (build container)"
+    reference_own_tests()
     ns = run("Laplace/00_laplace_with_rbf.py")
     g = rc.load("ref_laplace_demo_30x30")
     d, mse = rel(ns["sol"].vals, g["vals"]), float(np.mean(npa(ns["error"]) ** 2))

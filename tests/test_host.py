@@ -555,15 +555,26 @@ def test_small_host_utilities_of_the_reference_surface(tmp_path):
 
 def test_support_size_selects_only_the_global_path():
     """The reference turns 'max' into N (cloud.py:97-98) and then drops the node itself; N - 1 already drops the farthest
-    node of every support (RBF-FD), which is out of scope and must be refused, not silently treated as global."""
+    node of every support (RBF-FD), which is out of scope.  Such a cloud can be BUILT (geometry and numbering do not depend
+    on the supports; the reference's own test_interpolation.py builds one and only permutes fields) but assembling on it
+    is refused, not silently treated as global."""
     ft = {"South": "n", "West": "d", "North": "n", "East": "d"}
     for ss in ("max", None, 64):
-        assert u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss).N == 64
+        c = u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss)
+        assert c.N == 64 and c.support_size == 64 and len(c.local_supports[5]) == 63
+    full = u.SquareCloud(Nx=8, Ny=8, facet_types=ft)
     for ss in (63, 10):
+        c = u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss)
+        assert c.support_size == ss and np.array_equal(c.sorted_nodes, full.sorted_nodes) and c.facet_nodes == full.facet_nodes
+        assert c.local_supports[5] == full.local_supports[5][:ss - 1] and c.sorted_local_supports.shape == (64, ss - 1)
         with pytest.raises(NotImplementedError):
-            u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=ss)
+            asm.DeviceRows(c, asm.build_interpolation_rows(c))              # refused before any device work
+        with pytest.raises(NotImplementedError):
+            u.pde_solver_jit(laplace_op(u), lambda x, centers, rbf, fields: 0.0, c, {k: (lambda p: 0.0) for k in ft}, u.polyharmonic, 1)
     with pytest.raises(ValueError):
         u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size="all")
+    with pytest.raises(AssertionError):
+        u.SquareCloud(Nx=8, Ny=8, facet_types=ft, support_size=65)          # cloud.py:99-100
 
 
 def test_symbolic_and_numeric_lowering_agree_on_random_linear_operators():

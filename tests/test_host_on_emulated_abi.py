@@ -112,10 +112,12 @@ def test_randomised_solves_of_the_host_layer_against_oracle_assembled_systems():
 
 @needs_no_gpu
 def test_reference_demo_scripts_run_unmodified_on_the_product():
-    """demos/Laplace/00_laplace_with_rbf.py and demos/Darcy/00_darcy_flow.py of the reference executed as they are, with
+    """The reference's own three tests (updes/tests/test_*.py), then demos/Laplace/00_laplace_with_rbf.py,
+    demos/Darcy/00_darcy_flow.py and the projection loop of demos/NavierStokes/30_... of the reference executed as they are, with
     `updes` aliased to `updes_b200` (tests/run_reference_demo_on_product.py): same solution as the reference computed for
     the same script (1.4e-10 / 1.4e-8), same error figure printed (4.559171e-07 vs 4.559172e-07)."""
     if not os.path.isdir(REFERENCE):
         pytest.skip("needs /root/reference (build container)")
     out = _run("demos")
     assert "reference demos ran unmodified on the product" in out
+    assert "the reference's own 3 tests pass on the product" in out          # updes/tests/test_{interpolation,integrals,operators}.py

@@ -24,6 +24,11 @@ from .utils import RK4, dataloader, dot_mat, dot_vec, make_dir, plot, print_line
 import os  # noqa: E402,F401
 from functools import partial  # noqa: E402,F401
 from functools import partial as Partial  # noqa: E402,F401
+try:                                        # the reference's scripts also pick jax / jnp up from the star import
+    import jax  # noqa: E402,F401
+    import jax.numpy as jnp  # noqa: E402,F401
+except ImportError:                         # JAX is optional here (absent from this image): the product computes with numpy + CUDA
+    pass
 try:                                        # plt / sns reach the demos through the star import too; both are optional here
     import matplotlib.pyplot as plt  # noqa: E402,F401
 except ImportError:

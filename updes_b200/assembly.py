@@ -126,10 +126,21 @@ def build_interpolation_rows(cloud) -> RowTable:
                     np.arange(N, dtype=np.int32), N)
 
 
+def require_global_support(cloud):
+    """The product assembles the GLOBAL collocation system: every node in every support (``support_size="max"``, i.e. N).
+    A cloud built with a smaller support (RBF-FD, reference cloud.py:97-112) is refused here, before any device work."""
+    ss = getattr(cloud, "support_size", "max")
+    if ss not in ("max", None) and int(ss) != cloud.N:
+        raise NotImplementedError(
+            "updes_b200 implements the global collocation path only (support_size='max' or N = %d, got %d); "
+            "local RBF-FD supports are out of scope (reference README lists them as ill-conditioned)" % (cloud.N, int(ss)))
+
+
 class DeviceRows:
     """Row descriptors + centres resident in HBM, ready to hand to the C-ABI."""
 
     def __init__(self, cloud, table: RowTable, device="cuda"):
+        require_global_support(cloud)
         torch = _lib.require_cuda()
         self.torch = torch
         self.N = cloud.N

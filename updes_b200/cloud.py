@@ -24,8 +24,9 @@ import numpy as np
 class _LazySupports:
     """Read-only mapping node id -> list of the other nodes by increasing distance (ties by id), computed per access."""
 
-    def __init__(self, nodes):
+    def __init__(self, nodes, support_size=None):
         self._nodes = nodes
+        self._keep = (nodes.shape[0] if support_size is None else int(support_size)) - 1      # cloud.py:110-112: k nearest incl. self, self dropped
 
     def __len__(self):
         return self._nodes.shape[0]
@@ -47,7 +48,7 @@ class _LazySupports:
         d = self._nodes - self._nodes[i]
         d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
         order = np.lexsort((np.arange(n), d2))
-        return [int(j) for j in order if j != i]
+        return [int(j) for j in order if j != i][: self._keep]
 
     def items(self):
         return ((i, self[i]) for i in range(len(self)))
@@ -80,11 +81,13 @@ class Cloud:
     def _renumber(self, types, coords, normals_by_old, facet_nodes_old):
         """types: array of str per original id; returns the sorted arrays and fills the dicts."""
         req = getattr(self, "_requested_support", "max")
-        if req not in ("max", None) and int(req) != len(coords):
-            raise NotImplementedError(
-                "updes_b200 implements the global collocation path only (support_size='max' or N = %d, got %d); "
-                "local RBF-FD supports are out of scope (reference README lists them as ill-conditioned)" % (len(coords), int(req)))
         N = len(types)
+        # cloud.py:97-100: "max" means all N nodes.  A smaller support (RBF-FD) does not change the geometry built here,
+        # so the cloud itself is constructed (the reference's own test_interpolation.py asks for N - 1 and only permutes
+        # fields); assembling on it is refused (assembly.DeviceRows): the product implements the global path only.
+        self.support_size = N if req in ("max", None) else int(req)
+        if not 0 < self.support_size <= max(N, 1):
+            raise AssertionError("Support size must be strictly greater than 0 and at most the number of nodes")
         first = np.array([t[0] for t in types])
         order = [np.flatnonzero(first == c) for c in ("i", "d", "n", "r")]
         p_ids = np.flatnonzero(first == "p")
@@ -160,7 +163,8 @@ class Cloud:
         stores all N lists; here a list is computed when it is asked for (O(N log N) each), so a 250k-node cloud does not
         carry an (N, N - 1) table.  Equidistant nodes are ordered by node id (the reference takes BallTree's order there,
         which is implementation-defined)."""
-        return _LazySupports(self.sorted_nodes)
+        ss = getattr(self, "support_size", self.N)
+        return _LazySupports(self.sorted_nodes, self.N if ss in ("max", None) else int(ss))
 
     @property
     def sorted_local_supports(self):
@@ -168,7 +172,7 @@ class Cloud:
         if self.N > 20000:
             raise MemoryError("sorted_local_supports is an (N, N-1) table; the global path never needs it (N = %d)" % self.N)
         ls = self.local_supports
-        return np.array([ls[i] for i in range(self.N)], dtype=np.int64).reshape(self.N, max(self.N - 1, 0))
+        return np.array([ls[i] for i in range(self.N)], dtype=np.int64).reshape(self.N, -1) if self.N > 1 else np.zeros((self.N, 0), dtype=np.int64)
 
     def sort_dict_by_keys(self, dictionary):
         """cloud.py:72-81"""

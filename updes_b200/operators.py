@@ -940,6 +940,7 @@ def _digest(*arrays):
 def _interp_system(cloud, kind, param, M, distributed=None):
     """Factorisation of A = [[Phi P], [P^T 0]] (assembly.py:62-90), cached per (cloud, rbf, M).  On the
     multi-GPU path A is sharded like K (an (N+M)^2 matrix per rank would not fit at the sizes that path is for)."""
+    _asm.require_global_support(cloud)
     world, rank, group = _dist_world(distributed)
     key = ("A", id(cloud), kind, param, M, world, _DIST["grid"] if world > 1 else None)
     n = cloud.N + M
@@ -1020,6 +1021,7 @@ def pde_solver(diff_operator, rhs_operator, cloud, boundary_conditions, rbf, max
     the time loops of demos/Advection -- only pay for the right-hand side and two triangular sweeps.
     Keyword-only extras: ``refine`` (iterative-refinement steps, default 1), ``distributed`` (None = follow
     ``enable_distributed()``; True/False forces the sharded / single-GPU path for this call)."""
+    _asm.require_global_support(cloud)
     _mark("enter")
     kind, param = identify_rbf(rbf)
     robin_coeffs, boundary_conditions = duplicate_robin_coeffs(dict(boundary_conditions), cloud)
