@@ -30,6 +30,7 @@ Files (tests/golden/ref_*.npz), each with the cloud arrays and:
   ref_advection02_sink_2steps  demos/Advection/02_adv_diff_periodic_with_sink.py: its definitions (sink field through diff_args), two steps
   ref_grayscott001_2steps demos/Gray-Scott/001_gray-scott.py: periodic ids 'p0' / 'p1' with degree 1, two steps
   ref_wave00_2steps       demos/Wave/00_wave.py: all-Neumann cloud, polyharmonic a=3, degree 2, two nodal fields in the rhs, two steps
+  ref_cartesian_helpers   cartesian_gradient(_vec), enforce_cartesian_gradient_neumann, apply_neumann_conditions on three small clouds
   ref_config3_ns_2iter    config 3: two iterations of the demo's own projection loop (u, v, phi solves on the two mesh.msh clouds)
   ref_mesh_msh_{vel,phi}  the reference's fixture updes/tests/data/mesh.msh through GmshCloud for the two facet-type
                           sets of demos/NavierStokes/30_...:40-41; for phi also a row sample of bdPhi / bdP (Neumann
@@ -481,6 +482,34 @@ def case_wave00(nb_steps=2):
                 max_degree=np.array(ns["MAX_DEGREE"]), coeffs_last=npa(ufield.coeffs))
 
 
+def case_cartesian_helpers():
+    """cartesian_gradient / cartesian_gradient_vec / enforce_cartesian_gradient_neumann / apply_neumann_conditions
+    (operators.py:211-291, :483-509; called by demos/NavierStokes/11_...:187 and 16_...:181) on two square clouds and on a
+    generated channel mesh, for f = sin(3x) cos(2y) + x^2 and a fixed random gradient table."""
+    import tempfile
+    sys.path.insert(0, HERE)
+    from make_msh import write_channel_msh
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "channel.msh")
+        write_channel_msh(path, nx=9, ny=6)
+        clouds = [("sq_a", updes.SquareCloud(Nx=7, Ny=6, facet_types={"South": "n", "West": "d", "North": "d", "East": "n"}, support_size="max", noise_key=None)),
+                  ("sq_b", updes.SquareCloud(Nx=8, Ny=5, facet_types={"South": "d", "West": "n", "North": "r", "East": "d"}, support_size="max", noise_key=None)),
+                  ("msh", updes.GmshCloud(filename=path, facet_types={"Wall": "n", "Inflow": "d", "Outflow": "n"}))]
+        for tag, c in clouds:
+            xy = npa(c.sorted_nodes)
+            f = np.sin(3 * xy[:, 0]) * np.cos(2 * xy[:, 1]) + xy[:, 0] ** 2
+            g0 = np.random.default_rng(0).normal(size=(c.N, 2))
+            fj = jnp.array(f)
+            out[tag + "_nodes"] = xy
+            out[tag + "_f"], out[tag + "_g0"] = f, g0
+            out[tag + "_grad"] = npa(updes.cartesian_gradient_vec(range(c.N), fj, c))
+            out[tag + "_grad3_clipped"] = npa(updes.cartesian_gradient(3, fj, c, clip_val=0.05))
+            out[tag + "_enforced"] = npa(updes.enforce_cartesian_gradient_neumann(fj, jnp.array(g0), {}, c))
+            out[tag + "_applied"] = npa(updes.apply_neumann_conditions(fj, {}, c))
+    return out
+
+
 def case_config3(nb_iter=2):
     """Config 3 as the reference's demo runs it: the source text of simulate_forward_navier_stokes and its six operators
     is read from demos/NavierStokes/30_channel_flow_blowing_suction.py:61-250 and executed unchanged (the rest of that
@@ -505,7 +534,8 @@ CASES = {"ref_laplace_12x9": lambda: case_laplace(12, 9), "ref_robin_11x8": case
          "ref_mesh_msh_vel": lambda: case_mesh("vel"), "ref_mesh_msh_phi": lambda: case_mesh("phi"),
          "ref_integrals_12x12": case_integrals, "ref_laplace_demo_30x30": case_laplace_demo, "ref_darcy_demo_20x20": case_darcy_demo, "ref_config2_advdiff_3steps": case_config2, "ref_config3_ns_2iter": case_config3, "ref_multi_solver_9x8": case_multi, "ref_fuzz_16": case_fuzz, "ref_generated_msh": case_generated_msh,
          "ref_advection00_2steps": case_advection00, "ref_advection02_sink_2steps": case_advection02,
-         "ref_grayscott001_2steps": case_grayscott001, "ref_wave00_2steps": case_wave00}
+         "ref_grayscott001_2steps": case_grayscott001, "ref_wave00_2steps": case_wave00,
+         "ref_cartesian_helpers": case_cartesian_helpers}
 
 
 def main():

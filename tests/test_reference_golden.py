@@ -603,3 +603,29 @@ def test_oracle_matches_the_wave_demo_all_neumann_two_fields(oracle):
                              np.max(np.abs(vals - g["u"][s + 1])) / sc)
         print("wave demo step %d: reference-vs-exact %.2e, oracle-vs-exact %.2e, oracle-vs-reference %.2e" % (s, e_gold, e_ours, d))
         assert d <= max(1e-8, 4.0 * e_gold) and e_ours <= max(1e-8, 4.0 * e_gold)
+
+
+def test_cartesian_finite_difference_helpers_match_the_reference(tmp_path):
+    """cartesian_gradient(_vec), enforce_cartesian_gradient_neumann and apply_neumann_conditions (operators.py:211-291,
+    :483-509; demos/NavierStokes/11_...:187, 16_...:181) against what the reference returned on two square clouds and a
+    generated channel mesh -- including its quirks: the divisor of cartesian_gradient is the distance to the FARTHEST node of
+    the support (a variable left over from the loop), a node without a neighbour behind a direction returns early, and
+    enforce_... writes one number into both components."""
+    from golden.make_msh import write_channel_msh
+    g = rc.load("ref_cartesian_helpers")
+    path = str(tmp_path / "channel.msh")
+    write_channel_msh(path, nx=9, ny=6)
+    clouds = {"sq_a": u.SquareCloud(Nx=7, Ny=6, facet_types={"South": "n", "West": "d", "North": "d", "East": "n"}),
+              "sq_b": u.SquareCloud(Nx=8, Ny=5, facet_types={"South": "d", "West": "n", "North": "r", "East": "d"}),
+              "msh": u.GmshCloud(path, facet_types={"Wall": "n", "Inflow": "d", "Outflow": "n"})}
+    for tag, c in clouds.items():
+        assert np.array_equal(c.sorted_nodes, g[tag + "_nodes"])
+        f, g0 = g[tag + "_f"], g[tag + "_g0"]
+        grad = u.cartesian_gradient_vec(range(c.N), f, c)
+        assert np.allclose(grad, g[tag + "_grad"], rtol=1e-13, atol=1e-15), tag
+        assert np.any(np.all(grad == 0.0, axis=1)), "nodes with nothing behind +x return (0, 0)"
+        assert np.allclose(u.cartesian_gradient(3, f, c, clip_val=0.05), g[tag + "_grad3_clipped"], rtol=1e-13, atol=1e-15)
+        enforced = u.enforce_cartesian_gradient_neumann(f, g0, {}, c)
+        assert np.allclose(enforced, g[tag + "_enforced"], rtol=1e-13, atol=1e-15), tag
+        assert np.allclose(u.apply_neumann_conditions(f, {}, c), g[tag + "_applied"], rtol=0, atol=0), tag
+        assert np.array_equal(g0, g[tag + "_g0"]) and not np.shares_memory(enforced, g0)      # inputs are not modified

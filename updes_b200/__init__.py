@@ -8,7 +8,8 @@ sm_100a behind the C-ABI of include/updes_b200.h; there is no CPU fallback.
 from .cloud import Cloud, GmshCloud, SquareCloud
 from .rbf import (compute_nb_monomials, distance, gaussian, identify_rbf, inverse_multiquadric, make_all_monomials,
                   make_monomial, multiquadric, polyharmonic, thin_plate)
-from .operators import (BatchPoints, OperatorLoweringError, SteadySol, assemble_q, boundary_conditions_func_to_arr, clear_cache,
+from .operators import (apply_neumann_conditions, cartesian_gradient, cartesian_gradient_vec, enforce_cartesian_gradient_neumann,
+                        BatchPoints, OperatorLoweringError, SteadySol, assemble_q, boundary_conditions_func_to_arr, clear_cache,
                         disable_distributed, enable_distributed, integrate_field, interpolate_field,
                         compute_coefficients, core_compute_coefficients, divergence, divergence_vec, dot,
                         duplicate_robin_coeffs, get_field_coefficients, gradient, gradient_vals, gradient_vals_vec, gradient_vec,

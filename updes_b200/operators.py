@@ -1112,3 +1112,109 @@ def pde_multi_solver(diff_operators, rhs_operators, cloud, boundary_conditions, 
                                        rhs_args=None if rhs_args is None else rhs_args[i]) for i in range(n)]
         sols_vals = [s_.vals for s_ in sols]
     return sols
+
+
+# ==================================================================================================
+# Finite-difference helpers of the reference surface (host-only; operators.py:211-291, :483-509)
+# ==================================================================================================
+def _closest_opposite(cloud, ids, directions, chunk=2048):
+    """For every node ``ids[k]``: among the other nodes of its support whose unit offset u satisfies
+    ``dot(directions[k], u) + 1 <= 0.1`` (a cone around MINUS the direction), the closest one -- the primitive shared by
+    cartesian_gradient, enforce_cartesian_gradient_neumann and apply_neumann_conditions of the reference.  Returns
+    (index or -1, its distance, distance of the LAST node of the support list = the farthest node).  Equidistant
+    candidates: the reference keeps the last one in its support order (``<=``); here the one with the largest id."""
+    xy = np.asarray(cloud.sorted_nodes, dtype=np.float64)
+    ids = np.asarray(ids, dtype=np.int64)
+    directions = np.asarray(directions, dtype=np.float64).reshape(len(ids), 2)
+    keep = getattr(cloud, "support_size", cloud.N)
+    keep = cloud.N if keep in ("max", None) else int(keep)
+    close = np.full(len(ids), -1, dtype=np.int64)
+    cdist = np.full(len(ids), 1e20)
+    far = np.zeros(len(ids))
+    for lo in range(0, len(ids), chunk):
+        sl = slice(lo, min(lo + chunk, len(ids)))
+        off = xy[None, :, :] - xy[ids[sl], None, :]
+        nrm = np.sqrt(off[..., 0] ** 2 + off[..., 1] ** 2)
+        nrm[np.arange(sl.stop - sl.start), ids[sl]] = np.inf                          # the node itself is not in its support
+        if keep < cloud.N:                                                              # local supports: the keep - 1 nearest only
+            kth = np.partition(nrm, keep - 2, axis=1)[:, keep - 2]
+            nrm = np.where(nrm <= kth[:, None], nrm, np.inf)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cos = (off[..., 0] * directions[sl, 0:1] + off[..., 1] * directions[sl, 1:2]) / nrm
+        cand = np.where((cos + 1.0 <= 1e-1) & np.isfinite(nrm), nrm, np.inf)
+        best = cand.min(axis=1)
+        has = np.isfinite(best)
+        tie = cand == best[:, None]
+        pick = cloud.N - 1 - np.argmax(tie[:, ::-1], axis=1)                           # largest id among the closest
+        close[sl] = np.where(has, pick, -1)
+        cdist[sl] = np.where(has, best, 1e20)
+        far[sl] = np.where(np.isfinite(nrm), nrm, -np.inf).max(axis=1)
+    return close, cdist, far
+
+
+def cartesian_gradient_vec(node_ids, field, cloud):
+    """Backward differences towards the nearest node "behind" each axis direction (operators.py:211-259), as the reference
+    computes them: component d of node i is ``(field[i] - field[closest]) / vec_norm`` where ``vec_norm`` is left over from
+    the LAST iteration of the reference's loop over the support list -- the distance to the farthest node of the support,
+    not to the closest -- and a node with no neighbour behind direction d returns early with the remaining components 0.
+    Kept as written (demos/NavierStokes/11_...:187 and 16_...:181 call it).  Rows are indexed by node id, like there."""
+    node_ids = [int(i) for i in node_ids]
+    field = np.asarray(field, dtype=np.float64)
+    grad = np.zeros((len(node_ids), 2))
+    ids = np.asarray(node_ids, dtype=np.int64)
+    alive = np.ones(len(ids), dtype=bool)
+    for d, direction in ((0, (1.0, 0.0)), (1, (0.0, 1.0))):
+        close, _, far = _closest_opposite(cloud, ids, np.tile(direction, (len(ids), 1)))
+        alive &= close >= 0                                       # `return final_grad` as soon as a direction has no neighbour
+        vals = (field[ids] - field[np.where(close >= 0, close, 0)]) / far
+        grad[ids[alive], d] = vals[alive]
+    return grad
+
+
+def cartesian_gradient(node_id, field, cloud, clip_val=None):
+    """operators.py:211-252 for one node."""
+    return _clip(_cartesian_one(node_id, field, cloud), clip_val)
+
+
+def _cartesian_one(node_id, field, cloud):
+    field = np.asarray(field, dtype=np.float64)
+    i = int(node_id)
+    out = np.zeros(2)
+    for d, direction in ((0, (1.0, 0.0)), (1, (0.0, 1.0))):
+        close, _, far = _closest_opposite(cloud, [i], [direction])
+        if close[0] < 0:
+            return out
+        out[d] = (field[i] - field[close[0]]) / far[0]
+    return out
+
+
+def _neumann_nodes_and_normals(cloud):
+    ids = [i for f, t in cloud.facet_types.items() if t == "n" for i in cloud.facet_nodes[f]]
+    normals = np.array([np.asarray(cloud.outward_normals[i], dtype=np.float64) for i in ids]).reshape(len(ids), 2)
+    return np.asarray(ids, dtype=np.int64), normals
+
+
+def enforce_cartesian_gradient_neumann(field, grads, boundary_conditions, cloud, clip_val=None):
+    """operators.py:262-291: on every Neumann node, BOTH gradient components are overwritten by the one-sided difference
+    ``(field[i] - field[closest]) / distance`` towards the closest node opposite to the outward normal."""
+    field = np.asarray(field, dtype=np.float64)
+    grads = np.array(grads, dtype=np.float64, copy=True)
+    ids, normals = _neumann_nodes_and_normals(cloud)
+    if len(ids):
+        close, cdist, _ = _closest_opposite(cloud, ids, normals)
+        grads[ids] = ((field[ids] - field[close]) / cdist)[:, None] if grads.ndim == 2 else (field[ids] - field[close]) / cdist
+    return _clip(grads, clip_val)
+
+
+def apply_neumann_conditions(field, boundary_conditions, cloud):
+    """operators.py:483-509: every Neumann node takes the value of the closest node opposite to its outward normal (a
+    zero-flux condition imposed by copying; the boundary values themselves are not read, as in the reference)."""
+    field = np.array(field, dtype=np.float64, copy=True)
+    ids, normals = _neumann_nodes_and_normals(cloud)
+    if len(ids):
+        close, _, _ = _closest_opposite(cloud, ids, normals)
+        # the reference updates node after node, so a Neumann node whose closest neighbour is an EARLIER Neumann node
+        # reads the already updated value
+        for i, c in zip(ids, close):
+            field[i] = field[c]
+    return field
