@@ -647,3 +647,23 @@ def test_star_import_gives_a_reference_script_the_names_it_takes_from_updes():
     assert len({tuple(r) for r in rows}) == 9 and all(tuple(r) in {tuple(d) for d in data} for r in rows)
     assert [b.tolist() for b in u.dataloader(data, 3, 5)] == [b.tolist() for b in batches]   # same key, same batches
     assert list(u.dataloader(data, 10, 0)) == []
+
+
+def test_global_indices_hold_the_renumbered_ids_and_radial_profiles_match_the_kernels(capsys):
+    """cloud.py:153-157: after renumbering, global_indices[k, l] is the NEW id of grid node (k, l) (and global_indices_rev
+    its inverse); print_global_indices lays them out as drawn.  utils.py:30-89: the *_func radial profiles are what the
+    two-point kernels apply to the distance."""
+    c = u.SquareCloud(Nx=6, Ny=4, facet_types={"South": "p1", "West": "r", "North": "p1", "East": "n"})
+    xs, ys = np.linspace(0, 1, 6), np.linspace(0, 1, 4)
+    for k in range(6):
+        for l in range(4):
+            assert np.allclose(c.sorted_nodes[c.global_indices[k, l]], (xs[k], ys[l]), rtol=0, atol=1e-15)
+            assert c.global_indices_rev[int(c.global_indices[k, l])] == (k, l)
+    assert sorted(c.global_indices.ravel().tolist()) == list(range(c.N))
+    c.print_global_indices()
+    assert str(int(c.global_indices[0, 3])) in capsys.readouterr().out.splitlines()[0]          # top-left of the drawing
+    x, ctr = np.array([0.3, 0.4]), np.zeros(2)
+    assert u.polyharmonic(x, ctr, a=2) == u.polyharmonic_func(0.5, 2) and u.thin_plate(x, ctr, a=2) == u.thin_plate_func(0.5, 2)
+    assert u.gaussian(x, ctr, eps=3.0) == u.gaussian_func(0.5, 3.0) and u.multiquadric(x, ctr, eps=3.0) == u.multiquadric_func(0.5, 3.0)
+    assert u.inverse_multiquadric(x, ctr, eps=3.0) == u.inv_multiquadric_func(0.5, 3.0) and u.thin_plate_func(0.0, 1) == 0.0
+    assert u.make_nodal_rbf(x, ctr, lambda r: 2 * r) == 1.0 and u.value_vec_ is u.value and u.gradient_vec_ is u.gradient

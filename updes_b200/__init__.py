@@ -6,8 +6,9 @@ kernels, max_degree polynomial augmentation and Dirichlet / Neumann / Robin / pe
 sm_100a behind the C-ABI of include/updes_b200.h; there is no CPU fallback.
 """
 from .cloud import Cloud, GmshCloud, SquareCloud
-from .rbf import (compute_nb_monomials, distance, gaussian, identify_rbf, inverse_multiquadric, make_all_monomials,
-                  make_monomial, multiquadric, polyharmonic, thin_plate)
+from .rbf import (compute_nb_monomials, distance, gaussian, gaussian_func, identify_rbf, inv_multiquadric_func, inverse_multiquadric,
+                  make_all_monomials, make_monomial, make_nodal_rbf, multiquadric, multiquadric_func, polyharmonic, polyharmonic_func,
+                  thin_plate, thin_plate_func)
 from .operators import (apply_neumann_conditions, cartesian_gradient, cartesian_gradient_vec, enforce_cartesian_gradient_neumann,
                         BatchPoints, OperatorLoweringError, SteadySol, assemble_q, boundary_conditions_func_to_arr, clear_cache,
                         disable_distributed, enable_distributed, integrate_field, interpolate_field,
@@ -18,6 +19,8 @@ from .operators import (apply_neumann_conditions, cartesian_gradient, cartesian_
                         nodal_value, pde_multi_solver, pde_solver, pde_solver_jit, pde_solver_jit_with_bc, value, value_vec,
                         zerofy_periodic_cond)
 
+from .operators import value_vec_, gradient_vec_  # noqa: E402  (operators.py:149, :183: the un-jitted names)
+from .operators import gradient_vals_vec as gradient_vals_vec_, laplacian_vals_vec as laplacian_vals_vec_  # noqa: E402
 from .autodiff import linear_solve
 from .utils import RK4, dataloader, dot_mat, dot_vec, make_dir, plot, print_line_by_line, random_name
 # the reference's demo scripts take these names from `from updes import *` (updes/utils.py imports them at module level);

@@ -328,7 +328,7 @@ class SquareCloud(Cloud):
         gid = np.arange(self.N)
         I, J = gid // Ny, gid % Ny                       # cloud.py:411-422: gid = i*Ny + j
         self.global_indices = gid.reshape(Nx, Ny)
-        self.global_indices_rev = None                   # built lazily (dict of N tuples)
+        self.global_indices_rev = None
 
         # node types with the reference's facet precedence N, S, E, W (cloud.py:455-468)
         facet_of = np.full(self.N, "", dtype=object)
@@ -377,6 +377,13 @@ class SquareCloud(Cloud):
             for old in np.flatnonzero((facet_of == f) & np.isin(first, ["n", "r", "p"])):
                 normals[int(old)] = np.array(nv)
         self._renumber(types, coords, normals, facet_nodes_old)
+        # the reference renumbers its index grid too (cloud.py:153-157): global_indices[k, l] = the NEW id of grid node (k, l)
+        self.global_indices = self._new_of_old[gid].reshape(Nx, Ny)
+        self.global_indices_rev = {int(self.global_indices[k, l]): (k, l) for k in range(Nx) for l in range(Ny)} if self.N <= 20000 else None
+
+    def print_global_indices(self):
+        """cloud.py:51-58: the node ids laid out as the grid is drawn (y upwards)."""
+        print(np.flip(self.global_indices.T, axis=0))
 
 
 class GmshCloud(Cloud):

@@ -48,6 +48,36 @@ def thin_plate(x, center, a=1):
         return np.nan_to_num(np.log(r) * r ** (2 * a), nan=0.0, posinf=0.0, neginf=0.0)
 
 
+# radial profiles as functions of r (utils.py:30-66): what the kernels above apply to distance(x, center)
+def multiquadric_func(r, eps):
+    return np.sqrt(1 + (eps * np.asarray(r, dtype=np.float64)) ** 2)
+
+
+def inv_multiquadric_func(r, eps):
+    return 1.0 / np.sqrt(1 + (eps * np.asarray(r, dtype=np.float64)) ** 2)
+
+
+def gaussian_func(r, eps):
+    return np.exp(-(eps * np.asarray(r, dtype=np.float64)) ** 2)
+
+
+def polyharmonic_func(r, a):
+    return np.asarray(r, dtype=np.float64) ** (2 * a + 1)
+
+
+def thin_plate_func(r, a):
+    r = np.asarray(r, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.nan_to_num(np.log(r) * r ** (2 * a), nan=0.0, posinf=0.0, neginf=0.0)
+
+
+def make_nodal_rbf(x, node, rbf):
+    """utils.py:72-89: ``rbf`` given as a function of the distance, evaluated at |x - node| (polyharmonic when None -- the
+    reference then calls its two-point kernel with one argument and fails; here r^3)."""
+    r = distance(x, node)
+    return polyharmonic_func(r, 1) if rbf is None else rbf(r)
+
+
 for _f, _name in ((multiquadric, "multiquadric"), (inverse_multiquadric, "inverse_multiquadric"),
                   (gaussian, "gaussian"), (polyharmonic, "polyharmonic"), (thin_plate, "thin_plate")):
     _f.updes_kind = _name
