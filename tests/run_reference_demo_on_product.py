@@ -78,6 +78,19 @@ def reference_own_tests():
 def main():
     assert os.path.isdir(REFERENCE), "needs /root/reference (build container)"
     reference_own_tests()
+    # the README example (README.md:37-68, BASELINE.json configs[0]): the python block as printed there, executed literally
+    readme = open(os.path.join(REFERENCE, "README.md")).read()
+    block = readme[readme.index("```python") + len("```python"):]
+    block = block[:block.index("```")]
+    assert "import updes" in block and "pde_solver_jit" in block
+    ns = {}
+    updes_b200.clear_cache()
+    exec(compile(block, "README.md", "exec"), ns)
+    g = rc.load("ref_config1_30x20")
+    d = rel(ns["sol"].vals, g["vals"])
+    print("README.md example (config 1, 30x20), executed literally: solution vs the reference's pde_solver_jit %.2e" % d)
+    assert d <= 1e-8
+
     ns = run("Laplace/00_laplace_with_rbf.py")
     g = rc.load("ref_laplace_demo_30x30")
     d, mse = rel(ns["sol"].vals, g["vals"]), float(np.mean(npa(ns["error"]) ** 2))
