@@ -1117,7 +1117,7 @@ def pde_multi_solver(diff_operators, rhs_operators, cloud, boundary_conditions, 
 # ==================================================================================================
 # Finite-difference helpers of the reference surface (host-only; operators.py:211-291, :483-509)
 # ==================================================================================================
-def _closest_opposite(cloud, ids, directions, chunk=2048):
+def _closest_opposite(cloud, ids, directions, chunk=None):
     """For every node ``ids[k]``: among the other nodes of its support whose unit offset u satisfies
     ``dot(directions[k], u) + 1 <= 0.1`` (a cone around MINUS the direction), the closest one -- the primitive shared by
     cartesian_gradient, enforce_cartesian_gradient_neumann and apply_neumann_conditions of the reference.  Returns
@@ -1128,6 +1128,7 @@ def _closest_opposite(cloud, ids, directions, chunk=2048):
     directions = np.asarray(directions, dtype=np.float64).reshape(len(ids), 2)
     keep = getattr(cloud, "support_size", cloud.N)
     keep = cloud.N if keep in ("max", None) else int(keep)
+    chunk = chunk or max(1, 4_000_000 // max(cloud.N, 1))                     # a few (chunk, N) work arrays at a time
     close = np.full(len(ids), -1, dtype=np.int64)
     cdist = np.full(len(ids), 1e20)
     far = np.zeros(len(ids))
